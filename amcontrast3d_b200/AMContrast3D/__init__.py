@@ -1,0 +1,5 @@
+"""Host-side mirror of openpoints/AMContrast3D (Tier 3): same module names, class
+names, call signatures and return values as the reference, running on the sm_100a kernels."""
+from .MarginContrast import AmbiguityHead, ContrastHead
+from .MaskedRefine import RefinementMethod
+from .metrics import posmask_searching

@@ -1,0 +1,142 @@
+"""ctypes binding of libamc3d (include/amc3d.h) — the only door from Python to the kernels.
+
+There is deliberately no CPU fallback: if the shared library is missing or a call fails,
+this raises.  Device pointers come from ``tensor.data_ptr()``; the stream is torch's current
+stream on the tensor's device, so the kernels order correctly with surrounding torch work
+(the reference launches on the legacy default stream).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_longlong, c_void_p
+
+from . import _build
+
+_lock = threading.Lock()
+_lib = None
+
+
+class LossParams(Structure):
+    """struct amc3d_loss_params (include/amc3d.h)"""
+
+    _fields_ = [
+        ("temperature", c_float),
+        ("has_temperature", c_int),
+        ("margin_mode", c_int),
+        ("mu", c_float),
+        ("nu", c_float),
+        ("db_mode", c_int),
+        ("cl_method", c_int),
+    ]
+
+
+_P = c_void_p
+_I = c_int
+_F = c_float
+_LL = c_longlong
+
+# name -> argtypes (restype is always int unless listed in _RESTYPES)
+SIGNATURES = {
+    "amc3d_version": [],
+    "amc3d_arch": [],
+    "amc3d_last_error": [],
+    "amc3d_furthest_point_sampling": [_I, _I, _I, _P, _P, _P, _P],
+    "amc3d_ball_query": [_I, _I, _I, _F, _I, _P, _P, _P, _P],
+    "amc3d_group_points": [_I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "amc3d_group_points_ws": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "amc3d_group_points_grad": [_I, _I, _I, _I, _I, _P, _P, _P, _P],
+    "amc3d_group_points_grad_ws": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "amc3d_gather_points": [_I, _I, _I, _I, _P, _P, _P, _P],
+    "amc3d_gather_points_grad": [_I, _I, _I, _I, _P, _P, _P, _P],
+    "amc3d_three_nn": [_I, _I, _I, _P, _P, _P, _P, _P],
+    "amc3d_three_interpolate": [_I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "amc3d_three_interpolate_grad": [_I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "amc3d_knnquery": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "amc3d_grouping_forward": [_I, _I, _I, _P, _P, _P, _P],
+    "amc3d_grouping_backward": [_I, _I, _I, _P, _P, _P, _P],
+    "amc3d_stage_labels": [_I, _I, _I, _I, _LL, _P, _P, _P, _P],
+    "amc3d_posmask_count": [_I, _I, _I, _P, _P, _P, _P, _P, _P],
+    "amc3d_ambiguity": [_I, _I, _I, _P, _P, _P, _P, _P, _I, _F, _F, _P, _P, _P],
+    "amc3d_row_inv_norm": [_I, _I, _P, _P, _P],
+    "amc3d_amloss_forward": [_I, _I, _I, _I, _P, _P, _P, _P, _P, POINTER(LossParams), _P, _P, _P],
+    "amc3d_amloss_reduce": [_I, _P, _P, _P, _P],
+    "amc3d_amloss_backward": [_I, _I, _P, _P, _P, _P, _P, _I, _P, _P],
+    "amc3d_refine_select": [_I, _I, _I, _P, _P, _P, _P],
+    "amc3d_refine_forward": [_I, _I, _I, _P, _P, _P, _F, _F, _F, _P, _P, _P],
+    "amc3d_refine_backward": [_I, _I, _I, _P, _P, _P, _F, _F, _F, _P, _P],
+}
+_RESTYPES = {"amc3d_arch": c_char_p, "amc3d_last_error": c_char_p}
+
+
+class Amc3dError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return _build.LIBPATH
+
+
+def load(build_if_missing: bool = True) -> ctypes.CDLL:
+    """Load libamc3d_sm100a.so (building it with nvcc if absent).  Raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIBPATH
+        if not os.path.exists(path):
+            if not build_if_missing:
+                raise Amc3dError(f"{path} is missing: run `python -m amcontrast3d_b200._build`")
+            _build.build()
+        lib = ctypes.CDLL(path)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError = the library does not match the header
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, c_int)
+        if lib.amc3d_arch() != b"sm_100a":
+            raise Amc3dError("libamc3d was not built for sm_100a")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, name: str) -> None:
+    if rc != 0:
+        msg = load().amc3d_last_error().decode()
+        raise Amc3dError(f"{name} failed (code {rc}): {msg}")
+
+
+def call(name: str, *args) -> None:
+    """Invoke an int-returning entry point and raise on a non-zero code."""
+    check(getattr(load(), name)(*args), name)
+
+
+def ptr(t) -> int:
+    """Device pointer of a CUDA tensor (None -> NULL)."""
+    if t is None:
+        return 0
+    if not t.is_cuda:
+        raise Amc3dError("amc3d kernels need CUDA tensors: there is no CPU path in this package "
+                         "(the CPU restatement lives in oracle/ and is test infrastructure only)")
+    return t.data_ptr()
+
+
+def stream(t) -> int:
+    import torch
+
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+_NO_CPU = ("amc3d kernels need CUDA tensors: there is no CPU path in this package "
+           "(the CPU restatement lives in oracle/ and is test infrastructure only)")
+
+
+def guard(t):
+    """Device guard for the launch; refuses CPU tensors loudly."""
+    import torch
+
+    if not t.is_cuda:
+        raise Amc3dError(_NO_CPU)
+    return torch.cuda.device(t.device)

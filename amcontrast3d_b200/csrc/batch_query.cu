@@ -1,0 +1,173 @@
+// ball_query and three_nn on batched (B,N,3) clouds for sm_100a.
+//
+// Replaces openpoints/cpp/pointnet2_batch/src/ball_query_gpu.cu:15-73 and
+// interpolate_gpu.cu:16-81, where every thread streams the whole support cloud from global
+// memory with three scalar loads per point.  Here the support cloud of the batch element is
+// staged once per CTA through shared memory in the same grouped-SoA tiles as the kNN kernel
+// (one broadcast LDS.128 per 1.33 points), 256 queries per CTA.  Distances are the
+// reference expression bit for bit (common.cuh dist2_ref, operand order new - support).
+#include "common.cuh"
+
+namespace amc3d {
+
+constexpr int BQ_THREADS = 256;
+constexpr int BQ_TILE = 1024;
+constexpr int BQ_GROUPS = BQ_TILE / 4;
+
+__device__ __forceinline__ void load_tile_b(float4 *tile, const float *__restrict__ xyz, int t0,
+                                            int cnt) {
+    float *tf = reinterpret_cast<float *>(tile);
+    const int padded = (cnt + 3) & ~3;
+    for (int i = threadIdx.x; i < padded; i += blockDim.x) {
+        float x, y, z;
+        if (i < cnt) {
+            const float *p = xyz + 3ll * (t0 + i);
+            x = __ldg(p);
+            y = __ldg(p + 1);
+            z = __ldg(p + 2);
+        } else {
+            x = y = z = __int_as_float(0x7f800000);  // +inf: never inside a ball, never nearest
+        }
+        const int g = i >> 2, l = i & 3;
+        tf[g * 12 + l] = x;
+        tf[g * 12 + 4 + l] = y;
+        tf[g * 12 + 8 + l] = z;
+    }
+}
+
+// Semantics (ball_query_gpu.cu:29-50): scan k = 0..n-1; on a hit (d2 < r2, strict) with
+// cnt == 0 fill the whole row with k; idx[cnt++] = k; stop at nsample hits.  Rows without a
+// hit are not written.
+__global__ void __launch_bounds__(BQ_THREADS)
+ball_query_kernel(int n, int m, float radius, int nsample, const float *__restrict__ new_xyz,
+                  const float *__restrict__ xyz, int *__restrict__ idx) {
+    __shared__ float4 tile[BQ_GROUPS * 3];
+    const int b = blockIdx.y;
+    const int q = blockIdx.x * BQ_THREADS + threadIdx.x;
+    const bool active = q < m;
+    const int qq = active ? q : m - 1;
+    xyz += 3ll * b * n;
+    const float *qp = new_xyz + 3ll * ((long long)b * m + qq);
+    int *row = idx + ((long long)b * m + qq) * nsample;
+
+    const float r2 = __fmul_rn(radius, radius);
+    const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
+    int cnt = active ? 0 : nsample;  // inactive lanes count as finished
+    int first = -1;
+
+    for (int t0 = 0; t0 < n; t0 += BQ_TILE) {
+        const int tcnt = min(BQ_TILE, n - t0);
+        // the barrier doubles as the early exit: stop when every query of the CTA is full
+        if (__syncthreads_and(cnt >= nsample)) break;
+        load_tile_b(tile, xyz, t0, tcnt);
+        __syncthreads();
+        if (cnt >= nsample) continue;
+        const int groups = (tcnt + 3) >> 2;
+#pragma unroll 2
+        for (int g = 0; g < groups; ++g) {
+            const float4 X = tile[g * 3], Y = tile[g * 3 + 1], Z = tile[g * 3 + 2];
+            const float d0 = dist2_ref(qx - X.x, qy - Y.x, qz - Z.x);
+            const float d1 = dist2_ref(qx - X.y, qy - Y.y, qz - Z.y);
+            const float d2 = dist2_ref(qx - X.z, qy - Y.z, qz - Z.z);
+            const float d3 = dist2_ref(qx - X.w, qy - Y.w, qz - Z.w);
+            if (fminf(fminf(d0, d1), fminf(d2, d3)) < r2) {
+                const float dd[4] = {d0, d1, d2, d3};
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    if (dd[l] < r2 && cnt < nsample) {
+                        const int k = t0 + g * 4 + l;
+                        if (cnt == 0) first = k;
+                        row[cnt++] = k;
+                    }
+                }
+                if (cnt >= nsample) break;
+            }
+        }
+    }
+    if (active && first >= 0)
+        for (int l = cnt; l < nsample; ++l) row[l] = first;
+}
+
+// Semantics (interpolate_gpu.cu:37-58): ascending k, strict '<' cascade over three bests
+// initialised to 1e40 (double) / index 0.  Floats compared as doubles compare identically,
+// and (float)1e40 = +inf, so float bests initialised to +inf reproduce it exactly.
+__global__ void __launch_bounds__(BQ_THREADS)
+three_nn_kernel(int n, int m, const float *__restrict__ unknown, const float *__restrict__ known,
+                float *__restrict__ dist2, int *__restrict__ idx) {
+    __shared__ float4 tile[BQ_GROUPS * 3];
+    const int b = blockIdx.y;
+    const int q = blockIdx.x * BQ_THREADS + threadIdx.x;
+    const bool active = q < n;
+    const int qq = active ? q : n - 1;
+    known += 3ll * b * m;
+    const float *qp = unknown + 3ll * ((long long)b * n + qq);
+    const float ux = __ldg(qp), uy = __ldg(qp + 1), uz = __ldg(qp + 2);
+
+    const float inf = __int_as_float(0x7f800000);
+    float b1 = inf, b2 = inf, b3 = inf;
+    int i1 = 0, i2 = 0, i3 = 0;
+
+    for (int t0 = 0; t0 < m; t0 += BQ_TILE) {
+        const int tcnt = min(BQ_TILE, m - t0);
+        __syncthreads();
+        load_tile_b(tile, known, t0, tcnt);
+        __syncthreads();
+        const int groups = (tcnt + 3) >> 2;
+#pragma unroll 2
+        for (int g = 0; g < groups; ++g) {
+            const float4 X = tile[g * 3], Y = tile[g * 3 + 1], Z = tile[g * 3 + 2];
+            const float d0 = dist2_ref(ux - X.x, uy - Y.x, uz - Z.x);
+            const float d1 = dist2_ref(ux - X.y, uy - Y.y, uz - Z.y);
+            const float d2 = dist2_ref(ux - X.z, uy - Y.z, uz - Z.z);
+            const float d3 = dist2_ref(ux - X.w, uy - Y.w, uz - Z.w);
+            if (fminf(fminf(d0, d1), fminf(d2, d3)) < b3) {
+                const float dd[4] = {d0, d1, d2, d3};
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    const float d = dd[l];
+                    const int k = t0 + g * 4 + l;
+                    if (d < b1) {
+                        b3 = b2; i3 = i2;
+                        b2 = b1; i2 = i1;
+                        b1 = d;  i1 = k;
+                    } else if (d < b2) {
+                        b3 = b2; i3 = i2;
+                        b2 = d;  i2 = k;
+                    } else if (d < b3) {
+                        b3 = d;  i3 = k;
+                    }
+                }
+            }
+        }
+    }
+    if (active) {
+        const long long o = 3ll * ((long long)b * n + q);
+        dist2[o] = b1; dist2[o + 1] = b2; dist2[o + 2] = b3;
+        idx[o] = i1;   idx[o + 1] = i2;   idx[o + 2] = i3;
+    }
+}
+
+}  // namespace amc3d
+
+using namespace amc3d;
+
+extern "C" int amc3d_ball_query(int b, int n, int m, float radius, int nsample,
+                                const float *new_xyz, const float *xyz, int *idx, void *stream) {
+    AMC3D_REQUIRE(b >= 0 && n >= 0 && m >= 0 && nsample >= 1, AMC3D_EINVAL,
+                  "ball_query: bad sizes b=%d n=%d m=%d nsample=%d", b, n, m, nsample);
+    AMC3D_REQUIRE(b <= 65535, AMC3D_ELIMIT, "ball_query: batch %d > 65535", b);
+    if (b == 0 || m == 0 || n == 0) return 0;
+    dim3 grid(div_up(m, BQ_THREADS), b);
+    ball_query_kernel<<<grid, BQ_THREADS, 0, as_stream(stream)>>>(n, m, radius, nsample, new_xyz, xyz, idx);
+    return check_launch("ball_query");
+}
+
+extern "C" int amc3d_three_nn(int b, int n, int m, const float *unknown, const float *known,
+                              float *dist2, int *idx, void *stream) {
+    AMC3D_REQUIRE(b >= 0 && n >= 0 && m >= 0, AMC3D_EINVAL, "three_nn: bad sizes b=%d n=%d m=%d", b, n, m);
+    AMC3D_REQUIRE(b <= 65535, AMC3D_ELIMIT, "three_nn: batch %d > 65535", b);
+    if (b == 0 || n == 0) return 0;
+    dim3 grid(div_up(n, BQ_THREADS), b);
+    three_nn_kernel<<<grid, BQ_THREADS, 0, as_stream(stream)>>>(n, m, unknown, known, dist2, idx);
+    return check_launch("three_nn");
+}

@@ -1,0 +1,226 @@
+/*
+ * amc3d.h — C-ABI of the B200-native (sm_100a) point-grouping operators and the
+ * adaptive-margin contrastive loss of AMContrast3D.
+ *
+ * This is the drop-in boundary (Tier 1).  Every entry point takes plain
+ * device pointers, sizes and a CUDA stream (as void*; NULL = legacy default stream, which
+ * is what the reference launches on).  No torch types.  Outputs and scratch are allocated
+ * by the caller, exactly as in the reference, whose Python wrappers allocate every tensor
+ * and whose extension functions only borrow raw pointers for the duration of the launch.
+ *
+ * Return value: 0 on success, otherwise a negative AMC3D_E* code (argument errors) or the
+ * positive cudaError_t of the failed launch.  The reference calls exit(-1) on a launch
+ * failure (ball_query_gpu.cu:68-72, sampling_gpu.cu:255-259); a library must not, so the
+ * host side (amcontrast3d_b200/_capi.py) turns a non-zero return into a RuntimeError.
+ *
+ * "ref:" lines cite the reference interface each function replaces, relative to
+ * openpoints/cpp/ in YangChenApril/AMContrast3D.
+ */
+#ifndef AMC3D_H
+#define AMC3D_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMC3D_EINVAL (-1)   /* bad size / unsupported argument */
+#define AMC3D_ELIMIT (-2)   /* exceeds a documented limit (e.g. nsample > 128) */
+
+/* library / build identification; amc3d_version() returns AMC3D_VERSION */
+#define AMC3D_VERSION 100
+int amc3d_version(void);
+/* "sm_100a" — the only architecture this library is built for */
+const char *amc3d_arch(void);
+/* text of the last error on this thread (never NULL) */
+const char *amc3d_last_error(void);
+
+/* ---------------------------------------------------------------------------------------
+ * pointnet2_batch family: batched (B,N,3) xyz and (B,C,N) features, all contiguous f32/i32
+ * ------------------------------------------------------------------------------------- */
+
+/* Iterative farthest point sampling, first pick = index 0; ties resolved exactly as the
+ * reference's shared-memory tree (value desc, bit-reversed (k mod bs) asc, k asc).
+ * xyz (B,N,3); temp (B,N) running min-distance, read on entry (caller fills 1e10) and
+ * left holding the final distances; idx (B,m) i32.
+ * ref: pointnet2_batch/src/sampling.cpp:39 furthest_point_sampling_wrapper,
+ *      sampling_gpu.cu:218 furthest_point_sampling_kernel_launcher */
+int amc3d_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp,
+                                  int *idx, void *stream);
+
+/* First `nsample` support indices (ascending index) with d2 < radius^2; unfilled slots
+ * repeat the first hit; rows with no hit are left untouched (caller zero-fills idx).
+ * new_xyz (B,M,3) queries, xyz (B,N,3) support, idx (B,M,nsample) i32.
+ * ref: pointnet2_batch/src/ball_query.cpp:29 ball_query_wrapper_fast,
+ *      ball_query_gpu.cu:54 ball_query_kernel_launcher_fast */
+int amc3d_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz,
+                     const float *xyz, int *idx, void *stream);
+
+/* out[b,c,j,s] = points[b,c,idx[b,j,s]].  points (B,C,N), idx (B,npoints,nsample),
+ * out (B,C,npoints,nsample).
+ * ref: group_points.cpp:25 group_points_wrapper_fast, group_points_gpu.cu:75 */
+int amc3d_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
+                       const int *idx, float *out, void *stream);
+/* Same, with a caller-provided workspace of b*n*c floats (device).  With a workspace the
+ * gather runs through a channel-contiguous (B,N,C) copy of `points` (coalesced 128-byte
+ * reads, HBM-write bound); without one (NULL) a direct kernel is used. */
+int amc3d_group_points_ws(int b, int c, int n, int npoints, int nsample, const float *points,
+                          const int *idx, float *out, float *workspace, void *stream);
+
+/* grad_points[b,c,idx[b,j,s]] += grad_out[b,c,j,s]; grad_points (B,C,N) pre-zeroed by
+ * the caller.  ref: group_points.cpp:13 group_points_grad_wrapper_fast,
+ * group_points_gpu.cu:33 */
+int amc3d_group_points_grad(int b, int c, int n, int npoints, int nsample,
+                            const float *grad_out, const int *idx, float *grad_points,
+                            void *stream);
+/* Same, with a workspace of b*n*c floats: the scatter-add becomes warp-wide reductions onto
+ * 128 contiguous bytes of an L2-resident (B,N,C) accumulator, then a transpose-accumulate. */
+int amc3d_group_points_grad_ws(int b, int c, int n, int npoints, int nsample,
+                               const float *grad_out, const int *idx, float *grad_points,
+                               float *workspace, void *stream);
+
+/* out[b,c,j] = points[b,c,idx[b,j]].  ref: sampling.cpp:16, sampling_gpu.cu:33 */
+int amc3d_gather_points(int b, int c, int n, int npoints, const float *points,
+                        const int *idx, float *out, void *stream);
+/* grad_points[b,c,idx[b,j]] += grad_out[b,c,j].  ref: sampling.cpp:27, sampling_gpu.cu:72 */
+int amc3d_gather_points_grad(int b, int c, int n, int npoints, const float *grad_out,
+                             const int *idx, float *grad_points, void *stream);
+
+/* 3 nearest `known` points of each `unknown` point, ordered by (d2, index) ascending.
+ * unknown (B,n,3), known (B,m,3) -> dist2 (B,n,3) f32 (SQUARED; the Python wrapper takes
+ * the sqrt), idx (B,n,3) i32.  Fewer than 3 known points: remaining slots (+inf, 0).
+ * ref: interpolate.cpp:20 three_nn_wrapper_fast, interpolate_gpu.cu:62 */
+int amc3d_three_nn(int b, int n, int m, const float *unknown, const float *known,
+                   float *dist2, int *idx, void *stream);
+
+/* out[b,c,i] = w0*points[b,c,i0] + w1*points[b,c,i1] + w2*points[b,c,i2] (FMA chain as
+ * nvcc contracts the reference expression).  points (B,C,m), idx/weight (B,n,3).
+ * ref: interpolate.cpp:31, interpolate_gpu.cu:107 */
+int amc3d_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx,
+                            const float *weight, float *out, void *stream);
+/* grad_points[b,c,idx[b,i,t]] += grad_out[b,c,i]*weight[b,i,t]; grad_points pre-zeroed.
+ * ref: interpolate.cpp:45, interpolate_gpu.cu:152 */
+int amc3d_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out,
+                                 const int *idx, const float *weight, float *grad_points,
+                                 void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * pointops family: packed (n,3) xyz / (n,c) features with cumulative i32 `offset` ends
+ * ------------------------------------------------------------------------------------- */
+
+/* Exact k nearest neighbours inside each offset segment, ascending (d2, index).
+ * xyz (n,3) support, new_xyz (m,3) queries, offset/new_offset (nseg) device i32 cumulative
+ * ends, idx (m,nsample) i32, dist2 (m,nsample) f32 (SQUARED).  Segments shorter than
+ * nsample pad with (segment start, 1e10) like the reference.  nsample <= 128 (the
+ * reference's hard limit is 100, knnquery_cuda_kernel.cu:86-87).
+ * `n` and `nseg` are the sizes of xyz and offset, which the reference launcher does not
+ * take (it trusts the offsets); the Python shim passes xyz.shape[0] and offset.shape[0].
+ * ref: pointops/src/knnquery/knnquery_cuda.cpp:7 knnquery_cuda,
+ *      knnquery_cuda_kernel.cu:111 knnquery_cuda_launcher */
+int amc3d_knnquery(int n, int m, int nseg, int nsample, const float *xyz, const float *new_xyz,
+                   const int *offset, const int *new_offset, int *idx, float *dist2,
+                   void *stream);
+
+/* out[i,s,:] = in[idx[i,s],:].  in (n,c), idx (m,nsample), out (m,nsample,c).
+ * ref: pointops/src/grouping/grouping_cuda.cpp grouping_forward_cuda */
+int amc3d_grouping_forward(int m, int nsample, int c, const float *input, const int *idx,
+                           float *output, void *stream);
+/* grad_in[idx[i,s],:] += grad_out[i,s,:]; grad_in (n,c) pre-zeroed.
+ * ref: grouping_cuda.cpp grouping_backward_cuda */
+int amc3d_grouping_backward(int m, int nsample, int c, const float *grad_output,
+                            const int *idx, float *grad_input, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * adaptive-margin contrastive loss (one decoder stage)
+ * ref: openpoints/AMContrast3D/MarginContrast.py:220-259, AEF/ambiguity.py:11-93,
+ *      AEF/utils.py:11-43, AEF/function.py:10-39
+ * ------------------------------------------------------------------------------------- */
+
+/* Stage label by kNN vote: cls[i] = first argmax_c #{j<kr : t(nidx[i,j]) == c}, where
+ * t(x) = ncls-1 if has_ignore && target[x]==ignore_index else target[x].  kr == 0 means
+ * stage 0: cls[i] = t(i) (nidx unused).  target (M0) i64, nidx (m,kr) i32, cls (m) i32.
+ * ref: AEF/utils.py:11-43 get_subscene_label_CBL + MarginContrast.py:112 argmax */
+int amc3d_stage_labels(int m, int kr, int ncls, int has_ignore, long long ignore_index,
+                       const long long *target, const int *nidx, int *cls, void *stream);
+
+/* Neighbour lists below are given as (nbr, ld, ke): row i holds its ke neighbour indices at
+ * nbr[i*ld .. i*ld+ke).  For a kNN result knn_idx (m,k) whose column 0 is the self match
+ * (what the reference drops with [..., 1:], MarginContrast.py:226) pass nbr = knn_idx + 1,
+ * ld = k, ke = k-1 — no copy.  ke <= 32. */
+
+/* posmask bits and positive count: posbits (m) u32 (bit j set iff cls[i]==cls[nbr[i,j]]),
+ * cnt (m) i32, *max_cnt = max_i cnt[i] (device i32, zeroed by caller).
+ * ref: MarginContrast.py:226-231, AEF/ambiguity.py:13-14 */
+int amc3d_posmask_count(int m, int ke, int ld, const int *nbr, const int *cls, uint32_t *posbits,
+                        int *cnt, int *max_cnt, void *stream);
+
+/* Ambiguity a[i] (App. A.4 step 4).  cctype: 1 = Method1 (d+=d-=5), 2 = Method2 (sum of
+ * the reference's square_distance), 3 = Method3 (sum of sqrt(|d2|+1e-12)).
+ * stats (device i32[8], zeroed by caller): [0] #selected (0<a<=1), [1] #boundary,
+ * [2..6] the reference's five ambiguity bins (a==0, low, semi, high, ceil(10a)==10) for
+ * nu_m = nu*10.
+ * ref: AEF/ambiguity.py:11-93, AEF/function.py:10-39 */
+int amc3d_ambiguity(int m, int ke, int ld, const float *p, const int *nbr, const uint32_t *posbits,
+                    const int *cnt, const int *max_cnt, int cctype, float beta, float nu,
+                    float *a, int *stats, void *stream);
+
+/* inv[i] = 1 / max(||f_i||_2, 1e-8).  f (m,d) row-major. */
+int amc3d_row_inv_norm(int m, int d, const float *f, float *inv, void *stream);
+
+typedef struct amc3d_loss_params {
+    float temperature;   /* used when has_temperature != 0 */
+    int has_temperature;
+    int margin_mode;     /* 0 constant (nu), 1 adaptive (mu*a+nu) */
+    float mu, nu;
+    int db_mode;         /* 0 none, 1 '-m' (positives), 2 '+m' (negatives) */
+    int cl_method;       /* 1 = supervisedCL Method1, 2 = Method2 */
+} amc3d_loss_params;
+
+/* Fused loss forward + gradient accumulation for one stage.
+ * For every selected anchor (0<a<=1): cosine similarity to its k-1 neighbours, margin,
+ * temperature, exp/sums/log; writes -log r_i to loss_pt[i] (0 for unselected points);
+ * accumulates dL_i/du into ghat (m,d) (anchor role and neighbour role; ghat zeroed by the
+ * caller) WITHOUT the 1/|sel| factor.  Nothing of size m*k*d is materialised.
+ * f (m,d), inv (m), neighbour lists (nbr, ld, ke), posbits/a (m), loss_pt (m).
+ * ref: MarginContrast.py:77-79 dist_cos, :117-174 contrast_softnn_margin, :250-257 */
+int amc3d_amloss_forward(int m, int d, int ke, int ld, const float *f, const float *inv,
+                         const int *nbr, const uint32_t *posbits, const float *a,
+                         const amc3d_loss_params *params, float *loss_pt, float *ghat,
+                         void *stream);
+
+/* loss_out[0] = sum_i loss_pt[i] / stats[0]  (deterministic, double accumulation; the
+ * torch.mean over the selected points, MarginContrast.py:257; 0 selected -> NaN) */
+int amc3d_amloss_reduce(int m, const float *loss_pt, const int *stats, float *loss_out,
+                        void *stream);
+
+/* grad_f[r] = scale * (ghat[r] - u_r (u_r . ghat[r])) * inv[r] (norm >= 1e-8), where
+ * scale = upstream[0] / stats[0]  (upstream: device f32 scalar dTotal/dL_s; stats[0] =
+ * #selected from amc3d_ambiguity).  Accumulate=0 overwrites grad_f, 1 adds into it. */
+int amc3d_amloss_backward(int m, int d, const float *f, const float *inv, const float *ghat,
+                          const float *upstream, const int *stats, int accumulate,
+                          float *grad_f, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * AMContrast3D++ masked refinement (RefinementMethod.DualMasks, fusion 'MIN')
+ * ref: openpoints/AMContrast3D/MaskedRefine.py:49-119
+ * ------------------------------------------------------------------------------------- */
+
+/* jmin[r] = nbr[r, argmin_{j<ke} a[nbr[r,j]]] (first minimum); a (m). */
+int amc3d_refine_select(int m, int ke, int ld, const int *nbr, const float *a, int *jmin,
+                        void *stream);
+/* out = gamma*(f*~mask + cross*mask) + (1-gamma)*f over the (B,D,n) buffer, where
+ * cross is the flat D-float chunk jmin[r] of f re-viewed as (B,D,n) and mask[b,0,i] =
+ * thr <= a[b,i] <= thr_max.  update_count (device i32, zeroed by caller) += #mask. */
+int amc3d_refine_forward(int b, int d, int n, const float *f, const float *a, const int *jmin,
+                         float thr, float thr_max, float gamma, float *out,
+                         int *update_count, void *stream);
+/* grad_f for amc3d_refine_forward; grad_f (B,D,n) written (not accumulated) */
+int amc3d_refine_backward(int b, int d, int n, const float *grad_out, const float *a,
+                          const int *jmin, float thr, float thr_max, float gamma,
+                          float *grad_f, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMC3D_H */

@@ -1,0 +1,181 @@
+"""GPU parity of the adaptive-margin contrastive loss and the masked refinement against
+(a) the golden vectors produced by the reference's own Python code and (b) the torch
+restatement (oracle/loss_oracle.py), through the reference-facing module classes.
+
+Bars (BASELINE.json north_star): discrete outputs — stage labels, posmask, positive counts,
+the {0, 1, boundary} class of every ambiguity value, kNN indices — bit-exact; loss and
+gradients within 1e-5 relative.  The soft ambiguity values pass through FP32 pow() whose last
+bits differ between libm implementations (torch-CPU Sleef vs CUDA powf), so they are held to
+2e-6 relative instead of bit-exact; the tolerance is written next to each assert."""
+import numpy as np
+import pytest
+import torch
+
+from _util import GOLDEN_CASES, build_hierarchy, rel_err, stage_list_of
+from oracle import loss_oracle as lo
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+A_RTOL = 2e-6      # soft ambiguity values (pow ulps)
+LOSS_RTOL = 1e-5   # north_star tolerance for the loss
+GRAD_RTOL = 1e-5   # north_star tolerance for gradients (relative L2 per stage)
+
+
+def _check_ambiguity(a_gpu, a_ref):
+    a_gpu, a_ref = np.asarray(a_gpu), np.asarray(a_ref)
+    assert np.array_equal(a_gpu == 0, a_ref == 0)          # interior points
+    assert np.array_equal(a_gpu == 1, a_ref == 1)          # cnt == 0 points
+    assert np.allclose(a_gpu, a_ref, rtol=A_RTOL, atol=0)
+
+
+@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+def test_contrast_head_vs_reference_golden(golden, name):
+    from amcontrast3d_b200.AMContrast3D import ContrastHead
+    case = GOLDEN_CASES[name]
+    ncls, ign = case["num_classes"], case["ignore_index"]
+    p_list, f_list, target = build_hierarchy(num_classes=ncls, ignore_fraction=0.05 if ign is not None else 0.0)
+    sl = stage_list_of(p_list, f_list, device=DEV)
+    loss, a_cat, a_list = ContrastHead()(None, torch.from_numpy(target).to(DEV), sl, ncls, ign, case["args"])
+    loss.backward()
+    _check_ambiguity(a_cat.cpu().numpy(), golden[f"{name}/a_cat"])
+    assert abs(loss.item() - float(golden[f"{name}/loss"])) <= LOSS_RTOL * abs(float(golden[f"{name}/loss"]))
+    for s in range(4):
+        g = sl["up"][s]["f_out"].grad.cpu().numpy()
+        if f"{name}/grad{s}" in golden:
+            assert rel_err(g, golden[f"{name}/grad{s}"]) <= GRAD_RTOL
+        gn = float(golden[f"{name}/grad{s}_norm"])
+        assert abs(np.sqrt((g.astype(np.float64) ** 2).sum()) - gn) <= GRAD_RTOL * gn
+        rows = g[:: max(1, g.shape[0] // 16)][:16]
+        assert rel_err(rows, golden[f"{name}/grad{s}_rows"]) <= GRAD_RTOL
+
+
+def test_discrete_intermediates_bit_exact():
+    """labels, kNN indices, posmask and counts of every stage against the oracle"""
+    from amcontrast3d_b200.AMContrast3D.MarginContrast import _stage_ambiguity
+    from amcontrast3d_b200.AMContrast3D.AEF.utils import get_ftype
+    from amcontrast3d_b200 import _amloss
+    case = GOLDEN_CASES["scannet"]
+    p_list, f_list, target = build_hierarchy(num_classes=20, ignore_fraction=0.05, seed=21, n0=2048)
+    args = case["args"]
+    _, _, _, inter = lo.contrast_head_forward(torch.from_numpy(target), stage_list_of(p_list, f_list), 20, -100, args)
+    sl = stage_list_of(p_list, f_list, device=DEV, requires_grad=False)
+    nstride = torch.tensor([4, 4, 4, 4])
+    for s in range(4):
+        st = _stage_ambiguity("up", s, sl, torch.from_numpy(target).to(DEV), 20, -100, args, nstride,
+                              get_ftype("latent")[0])
+        ref = inter[s]
+        assert np.array_equal(st["cls"].cpu().numpy(), ref["cls"].numpy())
+        assert np.array_equal(st["knn_idx"].cpu().numpy(), ref["knn_idx"].numpy())
+        pm = _amloss.unpack_posmask(st["posbits"], st["nl"].ke).cpu().numpy()
+        assert np.array_equal(pm, ref["posmask"].numpy())
+        assert np.array_equal(st["cnt"].cpu().numpy(), ref["posmask"].sum(-1).numpy())
+        _check_ambiguity(st["a"].cpu().numpy(), ref["a"].numpy())
+        stats = st["stats"].cpu().numpy()
+        sel = ((ref["a"] > 0) & (ref["a"] <= 1)).sum().item()
+        assert stats[0] == sel
+
+
+@pytest.mark.parametrize("kind,k,dims", [("volume", 16, (64, 128, 256, 512)), ("surface", 32, (32, 64, 128, 256)),
+                                         ("volume", 9, (48, 100, 36, 20))])
+def test_contrast_head_vs_oracle(kind, k, dims):
+    """larger, boundary-rich scenes; also feature widths without a fused instantiation"""
+    from amcontrast3d_b200.AMContrast3D import ContrastHead
+    from _util import args_ns
+    args = args_ns(nsample=k)
+    p_list, f_list, target = build_hierarchy(seed=31, batch=2, n0=4096, dims=dims, kind=kind)
+    sl_ref = stage_list_of(p_list, f_list)
+    ref_loss, ref_a, _, _ = lo.contrast_head_forward(torch.from_numpy(target), sl_ref, 13, None, args)
+    ref_loss.backward()
+    sl = stage_list_of(p_list, f_list, device=DEV)
+    loss, a_cat, _ = ContrastHead()(None, torch.from_numpy(target).to(DEV), sl, 13, None, args)
+    (2.5 * loss).backward()                      # a non-unit upstream gradient
+    _check_ambiguity(a_cat.cpu().numpy(), ref_a.numpy())
+    assert abs(loss.item() - ref_loss.item()) <= LOSS_RTOL * abs(ref_loss.item())
+    for s in range(4):
+        g = sl["up"][s]["f_out"].grad.cpu().numpy() / 2.5
+        assert rel_err(g, sl_ref["up"][s]["f_out"].grad.numpy()) <= GRAD_RTOL
+
+
+def test_learned_margin_uses_torch_composition():
+    from amcontrast3d_b200.AMContrast3D import ContrastHead
+    from _util import args_ns
+    args = args_ns(margin="learned")
+    p_list, f_list, target = build_hierarchy(seed=5, n0=1024)
+    sl_ref = stage_list_of(p_list, f_list)
+    ref_loss, _, _, _ = lo.contrast_head_forward(torch.from_numpy(target), sl_ref, 13, None, args)
+    ref_loss.backward()
+    sl = stage_list_of(p_list, f_list, device=DEV)
+    loss, _, _ = ContrastHead()(None, torch.from_numpy(target).to(DEV), sl, 13, None, args)
+    loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= 1e-5 * abs(ref_loss.item())
+    assert rel_err(sl["up"][0]["f_out"].grad.cpu().numpy(), sl_ref["up"][0]["f_out"].grad.numpy()) <= 1e-4
+
+
+def test_ambiguity_head_and_api_functions(golden):
+    from amcontrast3d_b200.AMContrast3D import AmbiguityHead, posmask_searching
+    from amcontrast3d_b200.AMContrast3D.AEF.ambiguity import ambiguity_function
+    from amcontrast3d_b200.AMContrast3D.AEF.utils import get_subscene_label_CBL
+    case = GOLDEN_CASES["aa_default"]
+    p_list, f_list, target = build_hierarchy()
+    sl = stage_list_of(p_list, f_list, device=DEV, requires_grad=False)
+    tgt = torch.from_numpy(target).to(DEV)
+    a_list = AmbiguityHead()(tgt, sl, 13, None, case["args"])
+    _check_ambiguity(torch.cat(a_list).cpu().numpy(), golden["ambiguity_head/a_cat"])
+    nstride = torch.tensor([4, 4, 4, 4])
+    for s in range(4):
+        lab = get_subscene_label_CBL("up", s, sl, tgt, nstride, 13, None)
+        assert np.array_equal(lab.cpu().numpy(), golden[f"labels/stage{s}"])
+    pm, nidx = posmask_searching(sl["up"][0]["p_out"], tgt, 16, 13, None)
+    assert np.array_equal(pm.cpu().numpy(), golden["posmask_searching/posmask"])
+    assert np.array_equal(nidx.cpu().numpy(), golden["posmask_searching/nidx"])
+    # the reference-signature ambiguity_function on a given posmask / neighbour list
+    a, counts = ambiguity_function(sl["up"][0]["p_out"], pm, 15, nidx, "Method2", 0.04, False, 0.5)
+    ra, rcounts = lo.ambiguity_function(torch.from_numpy(p_list[0]), torch.from_numpy(golden["posmask_searching/posmask"]),
+                                        15, torch.from_numpy(golden["posmask_searching/nidx"]), "Method2", 0.04, 0.5)
+    _check_ambiguity(a.cpu().numpy(), ra.numpy())
+    assert counts == rcounts
+
+
+@pytest.mark.parametrize("tag,fusion,thr,thr_max,gamma", [
+    ("refine/MIN_0.9_0.4", "MIN", 0.9, 1.0, 0.4),
+    ("refine/MIN_0.5_1.0", "MIN", 0.5, 0.8, 1.0),
+    ("refine/MIN_ALL0_0.9_0.4", "MIN_ALL0", 0.9, 1.0, 0.4),
+])
+def test_dual_masks_vs_reference_golden(golden, tag, fusion, thr, thr_max, gamma):
+    from amcontrast3d_b200.AMContrast3D import RefinementMethod
+    p = torch.from_numpy(golden[f"{tag}/p"]).to(DEV)
+    f = torch.from_numpy(golden[f"{tag}/f"]).to(DEV).requires_grad_(True)
+    a = torch.from_numpy(golden[f"{tag}/a"]).to(DEV)
+    w = torch.from_numpy(golden[f"{tag}/w"]).to(DEV)
+    feat, rate = RefinementMethod({}, p, f, a, -1, p.shape[0], 8, fusion, thr_max, thr, gamma).DualMasks()
+    (feat * w).sum().backward()
+    if fusion == "MIN":
+        assert np.array_equal(feat.detach().cpu().numpy(), golden[f"{tag}/out"])     # copy + exact blend
+    else:
+        assert np.allclose(feat.detach().cpu().numpy(), golden[f"{tag}/out"], rtol=1e-6, atol=1e-7)
+    assert rate == float(golden[f"{tag}/rate"])
+    assert rel_err(f.grad.cpu().numpy(), golden[f"{tag}/grad"]) <= GRAD_RTOL
+
+
+def test_criteria_wrappers():
+    from amcontrast3d_b200.loss import build_criterion_from_cfg
+    from _util import args_ns
+    args = args_ns()
+    p_list, f_list, target = build_hierarchy(seed=9, n0=1024)
+    B, N = 2, 1024
+    logits = torch.from_numpy(np.random.default_rng(0).standard_normal((B, 13, N)).astype(np.float32))
+    sl_ref = stage_list_of(p_list, f_list)
+    ref_am, ref_a, _, _ = lo.contrast_head_forward(torch.from_numpy(target), sl_ref, 13, None, args)
+    ref_ce = torch.nn.functional.cross_entropy(logits.transpose(1, 2).reshape(-1, 13), torch.from_numpy(target))
+    ref = args.w1 * ref_ce + args.w2 * ref_am
+    sl = stage_list_of(p_list, f_list, device=DEV)
+    crit = build_criterion_from_cfg({"NAME": "CrossEntropyAce"})
+    out = crit(logits.to(DEV), torch.from_numpy(target).view(B, N).to(DEV), sl, 13, None, args)
+    assert abs(out.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    # AMContrast3D++ criterion with APM outputs
+    sl["ambiguity"] = [torch.rand(p.shape[0], 1, device=DEV) for p in p_list]
+    crit2 = build_criterion_from_cfg({"NAME": "CrossEntropyAcePre"})
+    total, ce, am, reg = crit2(logits.to(DEV), torch.from_numpy(target).view(B, N).to(DEV), sl, 13, None, args)
+    ref_reg = args.w3 * torch.nn.functional.l1_loss(torch.cat(sl["ambiguity"]).flatten().cpu(), ref_a)
+    assert abs(reg.item() - ref_reg.item()) <= 1e-5 * abs(ref_reg.item())
+    assert abs(total.item() - ref.item()) <= 1e-5 * abs(ref.item())

@@ -1,0 +1,260 @@
+"""GPU parity of the point-grouping operators against the CPU restatement of the reference
+kernels (oracle/ops_oracle.c), called through the reference-facing Python operators, which in
+turn go through the C-ABI of include/amc3d.h.  Bar: bit-exact indices / distances / gathers;
+scatter-add gradients within 1e-5 relative (the reference's own atomics are order-dependent)."""
+import numpy as np
+import pytest
+import torch
+
+from _util import rel_err
+from amcontrast3d_b200 import scenes
+from oracle import ops_oracle as oo
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+# ------------------------------------------------------------------ kNN
+@pytest.mark.parametrize("k", [1, 3, 4, 8, 12, 16, 24, 32, 33, 64, 100])
+def test_knn_single_segment(k):
+    from amcontrast3d_b200 import pointops
+    xyz, _ = scenes.surface_scene(6000, seed=3)
+    o = np.array([6000], dtype=np.int32)
+    ri, rd2 = oo.knnquery(k, xyz, None, o, o)
+    idx, dist = pointops.knnquery(k, _t(xyz), None, _t(o), _t(o))
+    assert idx.dtype == torch.int32 and dist.dtype == torch.float32
+    assert np.array_equal(idx.cpu().numpy(), ri)
+    assert np.array_equal(dist.cpu().numpy(), np.sqrt(rd2))
+
+
+def test_knn_raw_dist2_bit_exact_and_nsample_tensor():
+    from amcontrast3d_b200 import _amloss, pointops
+    xyz, _ = scenes.volume_scene(5000, seed=5)
+    o = np.array([5000], dtype=np.int32)
+    ri, rd2 = oo.knnquery(16, xyz, None, o, o)
+    idx, d2 = _amloss.knn_raw(16, _t(xyz), None, _t(o), _t(o))
+    assert np.array_equal(idx.cpu().numpy(), ri) and np.array_equal(d2.cpu().numpy(), rd2)
+    # nsample as a 0-dim tensor (AEF/utils.py:29 passes torch.prod(...))
+    idx2, _ = pointops.knnquery(torch.prod(torch.tensor([4, 4])), _t(xyz), _t(xyz), _t(o), _t(o))
+    assert np.array_equal(idx2.cpu().numpy(), ri)
+
+
+def test_knn_ragged_segments_and_cross_sets():
+    from amcontrast3d_b200 import pointops
+    rng = np.random.default_rng(0)
+    sizes = [700, 5, 1300, 259]            # one segment shorter than k
+    qsizes = [300, 40, 0, 513]             # an empty query segment
+    xyz = rng.random((sum(sizes), 3), dtype=np.float32) * 3
+    q = rng.random((sum(qsizes), 3), dtype=np.float32) * 3
+    o = np.cumsum(sizes).astype(np.int32)
+    qo = np.cumsum(qsizes).astype(np.int32)
+    for k in (8, 16, 40):
+        ri, rd2 = oo.knnquery(k, xyz, q, o, qo)
+        idx, dist = pointops.knnquery(k, _t(xyz), _t(q), _t(o), _t(qo))
+        assert np.array_equal(idx.cpu().numpy(), ri)
+        assert np.array_equal(dist.cpu().numpy(), np.sqrt(rd2))
+
+
+def test_knn_label_vote_shape():
+    """stage-0 support, sub-sampled queries, kr = 4/16/64 as in AEF/utils.py:29-36"""
+    from amcontrast3d_b200 import pointops
+    xyz, _ = scenes.surface_scene(8192, seed=9)
+    for kr, m in ((4, 2048), (16, 512), (64, 128)):
+        q = np.ascontiguousarray(xyz[:m])
+        o, qo = np.array([8192], dtype=np.int32), np.array([m], dtype=np.int32)
+        ri, rd2 = oo.knnquery(kr, xyz, q, o, qo)
+        idx, dist = pointops.knnquery(kr, _t(xyz), _t(q), _t(o), _t(qo))
+        assert np.array_equal(idx.cpu().numpy(), ri)
+
+
+def test_knn_empty_and_errors():
+    from amcontrast3d_b200 import _capi, pointops
+    xyz = _t(np.random.default_rng(1).random((100, 3), dtype=np.float32))
+    o = _t(np.array([100], dtype=np.int32))
+    idx, dist = pointops.knnquery(4, xyz, xyz[:0].contiguous(), o, _t(np.array([0], dtype=np.int32)))
+    assert idx.shape == (0, 4)
+    with pytest.raises(_capi.Amc3dError):
+        pointops.knnquery(200, xyz, xyz, o, o)        # beyond the documented nsample limit
+    with pytest.raises(_capi.Amc3dError):
+        pointops.knnquery(4, xyz.cpu(), None, o.cpu(), o.cpu())   # no CPU path
+
+
+def test_knn_full_size_properties():
+    """BASELINE config 2 size (8 x 24 000 points flattened into one segment): sortedness, self
+    match, and a sample of queries against the oracle."""
+    from amcontrast3d_b200 import _amloss
+    xyz, _ = scenes.batch_of_scenes(8, 24000, "surface")
+    flat = np.ascontiguousarray(xyz.reshape(-1, 3))
+    n = flat.shape[0]
+    o = np.array([n], dtype=np.int32)
+    idx, d2 = _amloss.knn_raw(16, _t(flat), None, _t(o), _t(o))
+    idx, d2 = idx.cpu().numpy(), d2.cpu().numpy()
+    assert (np.diff(d2, axis=1) >= 0).all()
+    assert (d2[:, 0] == 0).all()
+    sample = np.random.default_rng(0).choice(n, 1024, replace=False)
+    ri, rd2 = oo.knnquery(16, flat, np.ascontiguousarray(flat[sample]), o, np.array([1024], dtype=np.int32))
+    assert np.array_equal(d2[sample], rd2)
+    # overlapping scenes may contain exact distance ties; compare indices where the row is tie-free
+    tie_free = (np.diff(rd2, axis=1) > 0).all(1)
+    assert tie_free.mean() > 0.9
+    assert np.array_equal(idx[sample][tie_free], ri[tie_free])
+
+
+# ------------------------------------------------------------------ FPS
+@pytest.mark.parametrize("n,m,b", [(93, 23, 3), (375, 93, 2), (512, 128, 1), (1500, 375, 3), (2048, 512, 2),
+                                   (2049, 300, 2), (6000, 1500, 2), (8192, 600, 1), (24000, 6000, 2),
+                                   (24576, 400, 1)])
+def test_fps_matches_reference_sequence(n, m, b):
+    from amcontrast3d_b200.layers import furthest_point_sample
+    xyz, _ = scenes.batch_of_scenes(b, n, "surface", first_scene=n % 17)
+    ridx, _ = oo.fps(xyz, m)
+    idx = furthest_point_sample(_t(xyz), m)
+    assert idx.dtype == torch.int32 and tuple(idx.shape) == (b, m)
+    assert np.array_equal(idx.cpu().numpy(), ridx)
+
+
+@pytest.mark.parametrize("n,m", [(64000, 300), (70000, 64)])
+def test_fps_large_scenes(n, m):
+    """ScanNet-sized scenes: 16-CTA cluster path and the global-memory fallback"""
+    from amcontrast3d_b200.layers import furthest_point_sample
+    xyz, _ = scenes.batch_of_scenes(2, n, "volume", first_scene=2)
+    ridx, _ = oo.fps(xyz, m)
+    idx = furthest_point_sample(_t(xyz), m)
+    assert np.array_equal(idx.cpu().numpy(), ridx)
+
+
+@pytest.mark.parametrize("n,m", [(300, 120), (1500, 500), (5000, 700), (24000, 800)])
+def test_fps_exact_tie_order(n, m):
+    """Lattice points produce many exactly tied maxima; the winner must follow the reference's
+    shared-memory tree (bit-reversed thread order), which the oracle emulates literally."""
+    from amcontrast3d_b200.layers import furthest_point_sample
+    rng = np.random.default_rng(n)
+    xyz = rng.integers(0, 12, size=(2, n, 3)).astype(np.float32) * 0.25
+    ridx, rtemp = oo.fps(xyz, m)
+    from amcontrast3d_b200 import pointnet2_batch_cuda as ext
+    x = _t(xyz)
+    temp = torch.full((2, n), 1e10, device=DEV)
+    out = torch.zeros((2, m), dtype=torch.int32, device=DEV)
+    ext.furthest_point_sampling_wrapper(2, n, m, x, temp, out)
+    assert np.array_equal(out.cpu().numpy(), ridx)
+    assert np.array_equal(temp.cpu().numpy(), rtemp)        # temp is left holding the running distances
+    assert np.array_equal(furthest_point_sample(x, m).cpu().numpy(), ridx)
+
+
+# ------------------------------------------------------------------ ball query
+@pytest.mark.parametrize("n,m,r,ns", [(6000, 1500, 0.1, 32), (6000, 6000, 0.2, 32), (1500, 375, 0.4, 32),
+                                      (375, 93, 0.8, 16), (3000, 700, 0.02, 8), (2000, 2000, 5.0, 32)])
+def test_ball_query(n, m, r, ns):
+    from amcontrast3d_b200.layers import ball_query
+    xyz, _ = scenes.batch_of_scenes(3, n, "surface", first_scene=4)
+    q = np.ascontiguousarray(xyz[:, :m]) + (0.5 if r == 0.02 else 0.0)   # r=0.02 case: mostly empty balls
+    ref = oo.ball_query(r, ns, xyz, q)
+    idx = ball_query(r, ns, _t(xyz), _t(q))
+    assert idx.dtype == torch.int32
+    assert np.array_equal(idx.cpu().numpy(), ref)
+
+
+# ------------------------------------------------------------------ three_nn / interpolate
+@pytest.mark.parametrize("n,m", [(375, 93), (1500, 375), (6000, 1500), (700, 2), (50, 1)])
+def test_three_nn(n, m):
+    from amcontrast3d_b200.layers import three_nn
+    xyz, _ = scenes.batch_of_scenes(2, max(n, m), "surface", first_scene=6)
+    unknown, known = np.ascontiguousarray(xyz[:, :n]), np.ascontiguousarray(xyz[:, :m])
+    rd2, ri = oo.three_nn(unknown, known)
+    dist, idx = three_nn(_t(unknown), _t(known))
+    assert np.array_equal(idx.cpu().numpy(), ri)
+    assert np.array_equal(dist.cpu().numpy(), np.sqrt(rd2))
+
+
+def test_three_interpolate_forward_backward():
+    from amcontrast3d_b200.layers import three_interpolate, three_interpolation
+    rng = np.random.default_rng(2)
+    B, C, m, n = 2, 96, 375, 1500
+    xyz, _ = scenes.batch_of_scenes(B, n, "surface", first_scene=8)
+    known = np.ascontiguousarray(xyz[:, :m])
+    feats = rng.standard_normal((B, C, m)).astype(np.float32)
+    rd2, ri = oo.three_nn(xyz, known)
+    dist = np.sqrt(rd2)
+    recip = (1.0 / (dist + np.float32(1e-8))).astype(np.float32)
+    w = (recip / recip.sum(2, keepdims=True)).astype(np.float32)
+    f = _t(feats).requires_grad_(True)
+    out = three_interpolate(f, _t(ri), _t(w))
+    assert np.array_equal(out.detach().cpu().numpy(), oo.three_interpolate(feats, ri, w))
+    go = rng.standard_normal((B, C, n)).astype(np.float32)
+    out.backward(_t(go))
+    assert rel_err(f.grad.cpu().numpy(), oo.three_interpolate_grad(go, ri, w, m)) <= 1e-5
+    # composed operator, weights formed by torch on device exactly as upsampling.py:97-100
+    out2 = three_interpolation(_t(xyz), _t(known), _t(feats))
+    assert np.allclose(out2.cpu().numpy(), out.detach().cpu().numpy(), rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------ grouping
+@pytest.mark.parametrize("B,C,N,npoint,ns", [(2, 64, 6000, 1500, 32), (2, 128, 1500, 1500, 32), (3, 3, 6000, 1500, 32),
+                                             (1, 40, 375, 93, 16), (2, 7, 500, 100, 5), (1, 1024, 93, 93, 32)])
+def test_grouping_forward_backward(B, C, N, npoint, ns):
+    from amcontrast3d_b200.layers import grouping_operation
+    rng = np.random.default_rng(C)
+    feats = rng.standard_normal((B, C, N)).astype(np.float32)
+    idx = rng.integers(0, N, size=(B, npoint, ns)).astype(np.int32)
+    idx[:, :, ns // 2:] = idx[:, :, :1]          # ball-query style padding: repeated first hit
+    f = _t(feats).requires_grad_(True)
+    out = grouping_operation(f, _t(idx))
+    assert np.array_equal(out.detach().cpu().numpy(), oo.group_points(feats, idx))
+    go = rng.standard_normal(out.shape).astype(np.float32)
+    out.backward(_t(go))
+    assert rel_err(f.grad.cpu().numpy(), oo.group_points_grad(go, idx, N)) <= 1e-5
+
+
+def test_grouping_without_workspace_and_gather():
+    from amcontrast3d_b200 import _capi
+    from amcontrast3d_b200.layers import gather_operation
+    rng = np.random.default_rng(3)
+    B, C, N, npoint, ns = 2, 64, 2000, 500, 32
+    feats = rng.standard_normal((B, C, N)).astype(np.float32)
+    idx = rng.integers(0, N, size=(B, npoint, ns)).astype(np.int32)
+    f, i = _t(feats), _t(idx)
+    out = torch.empty((B, C, npoint, ns), device=DEV)
+    _capi.call("amc3d_group_points", B, C, N, npoint, ns, f.data_ptr(), i.data_ptr(), out.data_ptr(), 0)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), oo.group_points(feats, idx))
+    gidx = rng.integers(0, N, size=(B, 300)).astype(np.int32)
+    fg = _t(feats).requires_grad_(True)
+    g = gather_operation(fg, _t(gidx))
+    assert np.array_equal(g.detach().cpu().numpy(), oo.gather_points(feats, gidx))
+    go = rng.standard_normal(g.shape).astype(np.float32)
+    g.backward(_t(go))
+    assert rel_err(fg.grad.cpu().numpy(), oo.gather_points_grad(go, gidx, N)) <= 1e-5
+
+
+def test_query_and_group_module():
+    from amcontrast3d_b200.layers import create_grouper
+    xyz, _ = scenes.batch_of_scenes(2, 3000, "surface", first_scene=12)
+    q = np.ascontiguousarray(xyz[:, :750])
+    feats = np.random.default_rng(0).standard_normal((2, 32, 3000)).astype(np.float32)
+    grouper = create_grouper({"NAME": "ballquery", "radius": 0.15, "nsample": 32, "normalize_dp": True})
+    dp, fj = grouper(_t(q), _t(xyz), _t(feats))
+    idx = oo.ball_query(0.15, 32, xyz, q)
+    ref_xyz = oo.group_points(np.ascontiguousarray(xyz.transpose(0, 2, 1)), idx)
+    ref_dp = (ref_xyz - q.transpose(0, 2, 1)[..., None]) / np.float32(0.15)
+    assert np.array_equal(dp.cpu().numpy(), ref_dp.astype(np.float32))
+    assert np.array_equal(fj.cpu().numpy(), oo.group_points(feats, idx))
+
+
+def test_pointops_grouping_packed_layout():
+    from amcontrast3d_b200 import pointops
+    rng = np.random.default_rng(5)
+    n, c, m, ns = 3000, 64, 1000, 15
+    feats = rng.standard_normal((n, c)).astype(np.float32)
+    idx = rng.integers(0, n, size=(m, ns)).astype(np.int32)
+    f = _t(feats).requires_grad_(True)
+    out = pointops.grouping(f, _t(idx))
+    assert np.array_equal(out.detach().cpu().numpy(), feats[idx])
+    go = rng.standard_normal(out.shape).astype(np.float32)
+    out.backward(_t(go))
+    ref = np.zeros_like(feats)
+    np.add.at(ref, idx.reshape(-1), go.reshape(-1, c))
+    assert rel_err(f.grad.cpu().numpy(), ref) <= 1e-5
