@@ -108,9 +108,38 @@ def check(rc: int, name: str) -> None:
         raise Amc3dError(f"{name} failed (code {rc}): {msg}")
 
 
+# kernels launched by this package since import (bench.py reports the per-step delta as gpu_launches)
+LAUNCHES = 0
+# when set to a list, every call appends (name, start_event, stop_event) recorded on the launch stream
+PROFILE = None
+
+
+def _kernels_in(name: str, args) -> int:
+    if name == "amc3d_group_points_ws":
+        return 2 if args[-2] else 1            # transpose + gather with a workspace
+    if name == "amc3d_group_points_grad_ws":
+        return 2 if args[-2] else 1            # scatter + transpose-accumulate (plus a memset)
+    if name == "amc3d_refine_backward":
+        return 2
+    return 1
+
+
 def call(name: str, *args) -> None:
     """Invoke an int-returning entry point and raise on a non-zero code."""
-    check(getattr(load(), name)(*args), name)
+    global LAUNCHES
+    fn = getattr(load(), name)
+    if PROFILE is None:
+        check(fn(*args), name)
+    else:
+        import torch
+
+        st = torch.cuda.ExternalStream(args[-1]) if args[-1] else torch.cuda.default_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        check(fn(*args), name)
+        e1.record(st)
+        PROFILE.append((name, e0, e1, args[:6]))
+    LAUNCHES += _kernels_in(name, args)
 
 
 def ptr(t) -> int:

@@ -1,0 +1,164 @@
+"""Path replay: one training iteration's worth of hot-path calls, in the reference's call order.
+
+What a PointNeXt-XL / AMContrast3D step executes on this path,
+with random tensors standing in for the MLP outputs so that no cuDNN/cuBLAS work is timed:
+
+  encoder, level l = 1..4   furthest_point_sample(p_{l-1}, n_l) ; gather p_l
+                            QueryAndGroup(r_l, 32)(p_l, p_{l-1}, F_{l-1})          SetAbstraction
+                            (blocks_l - 1) x QueryAndGroup(2 r_l, 32)(p_l, p_l, F_l)   InvResMLP
+  decoder, level l = 4..1   three_interpolation(p_{l-1}, p_l, F_l)                 FeaturePropogation
+  criterion                 ContrastHead over the 4 stages {p_s (M_s,3), f_s (M_s,D_s), offset=[M_s]}
+  backward                  loss -> grad f_s ; grouping_operation scatter-add for the 19 feature
+                            groupings ; three_interpolate gradients
+  (AMContrast3D++)          RefinementMethod.DualMasks per decoder stage, forward + backward
+
+Every call goes through the reference-facing Python operators (amcontrast3d_b200.layers,
+.AMContrast3D), i.e. through the public API a user of the reference would call.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from . import scenes
+from .AMContrast3D import ContrastHead, RefinementMethod
+from .layers import QueryAndGroup, furthest_point_sample, three_interpolation
+
+# PointNeXt-XL as configured by cfgs/s3dis/AMContrast3D-AA.yaml:34-44
+XL = dict(blocks=(1, 4, 7, 4, 4), strides=(1, 4, 4, 4, 4), width=64, radius=0.1, nsample=32)
+
+
+def aa_args(nsample=16, **kw):
+    """ambiguity_args of cfgs/s3dis/AMContrast3D-AA.yaml:6-30 (nsample per BASELINE config)."""
+    d = dict(nsample=nsample, ccbeta=0.04, cctype="Method2", temperature=0.3, supervisedCL="Method1", db="-m",
+             margin="adaptive", mu=-1, nu=0.5, stages="up", stages_num=4, vis=False, w1=0.1, w2=0.9, w3=0.01)
+    d.update(kw)
+    return SimpleNamespace(**d)
+
+
+class PathReplay:
+    """Holds the synthetic inputs of one data-parallel unit (B scenes flattened into one segment
+    by the encoder, pointnext_AA.py:458-462) and replays the hot path over them."""
+
+    def __init__(self, batch=8, n_points=24000, device="cuda", k=16, num_classes=13, ignore_index=None,
+                 kind="surface", rank=0, first_scene=0, arch=XL, refine=False, refine_k=12, seed=0,
+                 with_grouping=True, with_loss=True):
+        self.B, self.N, self.device = batch, n_points, torch.device(device)
+        self.num_classes, self.ignore_index = num_classes, ignore_index
+        self.args = aa_args(k)
+        self.arch = arch
+        self.refine, self.refine_k = refine, refine_k
+        self.with_grouping, self.with_loss = with_grouping, with_loss
+        xyz, labels = scenes.batch_of_scenes(batch, n_points, kind, rank=rank, first_scene=first_scene,
+                                             num_classes=num_classes,
+                                             ignore_fraction=0.05 if ignore_index is not None else 0.0)
+        # host side of the step: pinned xyz + labels (what the trainer's H2D copy moves, main_AA.py:377-379)
+        self.h_xyz = torch.from_numpy(xyz).pin_memory() if torch.cuda.is_available() else torch.from_numpy(xyz)
+        self.h_labels = torch.from_numpy(labels).pin_memory() if torch.cuda.is_available() else torch.from_numpy(labels)
+        self.h2d_bytes = self.h_xyz.numel() * 4 + self.h_labels.numel() * 8
+        self.d_xyz = self.h_xyz.to(self.device)
+        self.d_labels = self.h_labels.to(self.device)
+
+        nlev = len(arch["blocks"])
+        self.n = [n_points]
+        self.C = [arch["width"]]
+        for l in range(1, nlev):
+            self.n.append(self.n[-1] // arch["strides"][l])
+            self.C.append(self.C[-1] * 2)
+        g = torch.Generator(device=self.device)
+        g.manual_seed(1234 + seed + 7919 * rank)
+        # F_l: stand-ins for the MLP outputs at each level, (B, C_l, n_l), require grad
+        self.F = [torch.randn((batch, self.C[l], self.n[l]), device=self.device, generator=g).requires_grad_(True)
+                  for l in range(nlev)]
+        # decoder features feeding the loss, (M_s, D_s) row-major, require grad
+        self.f_dec = [torch.randn((batch * self.n[s], self.C[s]), device=self.device, generator=g).requires_grad_(True)
+                      for s in range(4)]
+        r = arch["radius"]
+        self.sa = [None] + [QueryAndGroup(r * 2 ** (l - 1), arch["nsample"], normalize_dp=True) for l in range(1, nlev)]
+        self.la = [None] + [QueryAndGroup(r * 2 ** l, arch["nsample"], normalize_dp=True) for l in range(1, nlev)]
+        self.head = ContrastHead()
+        # synthetic upstream gradients: one buffer, viewed per output
+        self._gbuf = None
+        self.points_per_step = batch * n_points
+
+    # ------------------------------------------------------------------------------------
+    def _grad_like(self, t):
+        n = t.numel()
+        if self._gbuf is None or self._gbuf.numel() < n:
+            self._gbuf = torch.randn(n, device=self.device)
+        return self._gbuf[:n].view(t.shape)
+
+    def zero_grads(self):
+        for t in self.F + self.f_dec:
+            t.grad = None
+
+    def forward(self, xyz=None, labels=None):
+        """-> (loss, outputs needing a synthetic upstream gradient)"""
+        p0 = self.d_xyz if xyz is None else xyz
+        labels = self.d_labels if labels is None else labels
+        arch = self.arch
+        p = [p0]
+        outs = []
+        for l in range(1, len(arch["blocks"])):
+            idx = furthest_point_sample(p[l - 1], self.n[l]).long()
+            p.append(torch.gather(p[l - 1], 1, idx.unsqueeze(-1).expand(-1, -1, 3)).contiguous())
+            if self.with_grouping:
+                dp, fj = self.sa[l](p[l], p[l - 1], self.F[l - 1])
+                outs.append(fj)
+                for _ in range(arch["blocks"][l] - 1):
+                    dp, fj = self.la[l](p[l], p[l], self.F[l])
+                    outs.append(fj)
+        for l in range(len(arch["blocks"]) - 1, 0, -1):
+            outs.append(three_interpolation(p[l - 1], p[l], self.F[l]))
+        loss = None
+        if self.with_loss:
+            feats = self.f_dec
+            if self.refine:
+                feats = []
+                for s in range(4):
+                    B, n_s, D = self.B, self.n[s], self.C[s]
+                    f_bdn = self.f_dec[s].view(B, n_s, D).transpose(1, 2).contiguous()
+                    a = self._apm[s]
+                    f_ref, _ = RefinementMethod({}, p[s], f_bdn, a, s, B, self.refine_k, "MIN", 1.0, 0.9, 0.4).DualMasks()
+                    feats.append(f_ref.transpose(1, 2).reshape(B * n_s, D))
+            down = [{"p_out": p[s].reshape(-1, 3), "f_out": feats[s],
+                     "offset": self._offsets[s]} for s in range(4)]
+            stage_list = {"inputs": None, "down": down, "up": down}
+            loss, a_cat, _ = self.head(None, labels.reshape(-1), stage_list, self.num_classes, self.ignore_index,
+                                       self.args)
+        return loss, outs
+
+    @property
+    def _offsets(self):
+        if not hasattr(self, "_off"):
+            self._off = [torch.tensor([self.B * self.n[s]], dtype=torch.int32, device=self.device) for s in range(4)]
+        return self._off
+
+    @property
+    def _apm(self):
+        if not hasattr(self, "_apm_a"):
+            g = torch.Generator(device=self.device)
+            g.manual_seed(99)
+            self._apm_a = [torch.rand((self.B, 1, self.n[s]), device=self.device, generator=g) for s in range(4)]
+        return self._apm_a
+
+    def step(self, xyz=None, labels=None):
+        """forward + backward of the path; returns the loss tensor (device scalar)"""
+        self.zero_grads()
+        loss, outs = self.forward(xyz, labels)
+        tensors = list(outs)
+        grads = [self._grad_like(o) for o in outs]
+        if loss is not None:
+            tensors.append(loss)
+            grads.append(None)
+        torch.autograd.backward(tensors, grads)
+        return loss
+
+    def step_e2e(self):
+        """The same step driven from HOST buffers: pinned xyz/labels -> device, step, loss -> host."""
+        xyz = self.h_xyz.to(self.device, non_blocking=True)
+        labels = self.h_labels.to(self.device, non_blocking=True)
+        loss = self.step(xyz, labels)
+        return float(loss.item()) if loss is not None else 0.0

@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py — scene-points/s of the AMContrast3D hot path (FPS + ball query/kNN + grouping + AM loss
+fwd/bwd) on 1..8 B200, next to the reference algorithm on the host CPU cores.
+
+    python bench.py --gpus 1 --steps K --warmup W            # this repo's sm_100a kernels
+    python bench.py --impl reference --steps K --warmup W     # CPU restatement of the reference (oracle/)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one data-parallel unit = BASELINE config 2: 8 S3DIS-shaped
+scenes x 24 000 points through the PointNeXt-XL grouping operators and the AMContrast3D-AA loss,
+forward + backward (amcontrast3d_b200/replay.py).  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "scene-points/sec (FPS+kNN+group+AM loss fwd/bwd)"
+UNIT = "scene-points/s"
+WORKLOAD = "PointNeXt-XL grouping ops + AMContrast3D-AA loss fwd/bwd, unit = 8 x 24000-pt S3DIS-shaped scenes"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.proc, self.index = None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm restated in oracle/ (C for the operators, torch for the loss)
+# ------------------------------------------------------------------------------------------
+def cpu_path_replay(xyz, labels, k=16, seed=0):
+    """One scene (1, N, 3) through the same call sequence as replay.PathReplay.step, on the host.
+    Returns the loss value.  Executes oracle/ — allowed here only as the measured CPU baseline."""
+    from amcontrast3d_b200.replay import XL, aa_args
+    from oracle import loss_oracle as lo
+    from oracle import ops_oracle as oo
+    rng = np.random.default_rng(seed)
+    B, N, _ = xyz.shape
+    n, C = [N], [XL["width"]]
+    for l in range(1, 5):
+        n.append(n[-1] // XL["strides"][l])
+        C.append(C[-1] * 2)
+    F = [rng.standard_normal((B, C[l], n[l]), dtype=np.float32) for l in range(5)]
+    p = [xyz]
+    grouped = []
+    for l in range(1, 5):
+        idx, _ = oo.fps(p[l - 1], n[l])
+        p.append(np.take_along_axis(p[l - 1], idx[:, :, None].astype(np.int64), axis=1))
+        r = XL["radius"] * 2 ** (l - 1)
+        bq = oo.ball_query(r, 32, p[l - 1], p[l])
+        oo.group_points(np.ascontiguousarray(p[l - 1].transpose(0, 2, 1)), bq)
+        grouped.append((oo.group_points(F[l - 1], bq), bq, n[l - 1]))
+        for _ in range(XL["blocks"][l] - 1):
+            bq = oo.ball_query(2 * r, 32, p[l], p[l])
+            oo.group_points(np.ascontiguousarray(p[l].transpose(0, 2, 1)), bq)
+            grouped.append((oo.group_points(F[l], bq), bq, n[l]))
+    ups = []
+    for l in range(4, 0, -1):
+        d2, i3 = oo.three_nn(p[l - 1], p[l])
+        recip = 1.0 / (np.sqrt(d2) + np.float32(1e-8))
+        w = (recip / recip.sum(2, keepdims=True)).astype(np.float32)
+        ups.append((oo.three_interpolate(F[l], i3, w), i3, w, n[l]))
+    p_list = [pp.reshape(-1, 3) for pp in p[:4]]
+    f_list = [torch.from_numpy(rng.standard_normal((B * n[s], C[s]), dtype=np.float32)).requires_grad_(True)
+              for s in range(4)]
+    sl = lo.make_stage_list([torch.from_numpy(np.ascontiguousarray(pp)) for pp in p_list], f_list)
+    loss, _, _, _ = lo.contrast_head_forward(torch.from_numpy(labels.reshape(-1)), sl, 13, None, aa_args(k))
+    loss.backward()
+    for out, bq, nn in grouped:       # scatter-add backward of the 19 feature groupings
+        oo.group_points_grad(out, bq, nn)
+    for out, i3, w, m in ups:
+        oo.three_interpolate_grad(out, i3, w, m)
+    return float(loss.item())
+
+
+def time_cpu_sample(steps, warmup, k=16):
+    from amcontrast3d_b200 import scenes
+    from oracle import ops_oracle as oo
+    cores = oo.host_threads()
+    torch.set_num_threads(cores)
+    xyz, labels = scenes.batch_of_scenes(1, 24000, "surface")
+    for _ in range(warmup):
+        cpu_path_replay(xyz, labels, k)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        cpu_path_replay(xyz, labels, k)
+        times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    return 24000 / (ms / 1e3), ms, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, ms, cores = time_cpu_sample(max(1, args.steps), args.warmup)
+    sample = ("1 scene x 24000 pts per step through the full path (FPS, 19 ball queries, 38 groupings, "
+              "three_nn/interpolate, AA loss fwd+bwd, grouping/interpolate backward); B=1 so its kNN does 1/8 "
+              "of the pairs per point of the B=8 unit (favours the CPU)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "k": 16, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# per-kernel accounting for the roofline object
+# ------------------------------------------------------------------------------------------
+def algorithmic_work(name, a):
+    """(kind, amount) of algorithmic work of one C-ABI call from its leading int arguments.
+    kind 'flop' -> FP32 FLOP (8 per pair: 3 sub, 3 mul, 2 add — BASELINE.md §4); 'byte' -> HBM bytes."""
+    if name == "amc3d_knnquery":
+        n, m = a[0], a[1]
+        return "flop", 8.0 * n * m
+    if name in ("amc3d_ball_query", "amc3d_three_nn"):
+        b, n, m = a[0], a[1], a[2]
+        return "flop", 8.0 * b * n * m
+    if name in ("amc3d_group_points_ws", "amc3d_group_points"):
+        b, c, n, npnt, ns = a[:5]
+        return "byte", 4.0 * b * (c * npnt * ns + c * n + npnt * ns)
+    if name in ("amc3d_group_points_grad_ws", "amc3d_group_points_grad"):
+        b, c, n, npnt, ns = a[:5]
+        return "byte", 4.0 * b * (c * npnt * ns + 2 * c * n + npnt * ns)
+    if name == "amc3d_three_interpolate":
+        b, c, m, n = a[:4]
+        return "byte", 4.0 * b * (c * n + c * m + 6 * n)
+    if name == "amc3d_three_interpolate_grad":
+        b, c, n, m = a[:4]
+        return "byte", 4.0 * b * (c * n + 2 * c * m + 6 * n)
+    return None, 0.0
+
+
+def profile_step(replay):
+    """One extra, untimed step with CUDA events around every C-ABI call -> per-entry totals."""
+    from amcontrast3d_b200 import _capi
+    torch.cuda.synchronize()
+    _capi.PROFILE = []
+    replay.step()
+    torch.cuda.synchronize()
+    prof, _capi.PROFILE = _capi.PROFILE, None
+    agg = {}
+    for name, e0, e1, a in prof:
+        ms = e0.elapsed_time(e1)
+        kind, amount = algorithmic_work(name, a)
+        d = agg.setdefault(name, {"calls": 0, "ms": 0.0, "flop": 0.0, "byte": 0.0})
+        d["calls"] += 1
+        d["ms"] += ms
+        if kind:
+            d[kind] += amount
+    return agg
+
+
+def fp32_peak_tflops():
+    """Nominal non-tensor FP32 peak of a B200: 148 SMs x 128 lanes x 2 FLOP x max SM clock."""
+    try:
+        mhz = float(subprocess.run(["nvidia-smi", "--query-gpu=clocks.max.sm", "--format=csv,noheader,nounits",
+                                    "-i", "0"], capture_output=True, text=True).stdout.split()[0])
+    except Exception:
+        mhz = 1965.0
+    return 148 * 128 * 2 * mhz * 1e6 / 1e12
+
+
+def run_ours(args):
+    from amcontrast3d_b200 import _capi
+    from amcontrast3d_b200 import dist as amdist
+    from amcontrast3d_b200.replay import PathReplay
+    import torch.distributed as tdist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device for --impl ours: this package has no CPU path")
+    rank, local, world = amdist.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _capi.load(build_if_missing=False)
+
+    replay = PathReplay(batch=args.batch, n_points=args.points, device=dev, k=args.k, rank=rank)
+    stats_layout = amdist.PackedStats(13)
+    buckets = amdist.GradBuckets(int(args.grad_mb * 1e6 / 4), dev) if world > 1 and args.grad_mb > 0 else None
+
+    def one_step(e2e=False):
+        if e2e:
+            xyz = replay.h_xyz.to(dev, non_blocking=True)
+            labels = replay.h_labels.to(dev, non_blocking=True)
+            loss = replay.step(xyz, labels)
+        else:
+            loss = replay.step()
+        if world > 1:
+            if buckets is not None:
+                buckets.launch()
+            z = torch.zeros(13, device=dev)
+            buf = stats_layout.pack_device(loss, loss, loss, torch.zeros(4, device=dev), z, z, z)
+            amdist.all_reduce_packed(buf)
+            if buckets is not None:
+                buckets.wait()
+        return loss
+
+    def timed(n_steps, e2e):
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for _ in range(n_steps):
+            loss = one_step(e2e)
+            if e2e:
+                last = float(loss.item())        # device -> host read of the step's result
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+            ms = t.item()
+            tdist.barrier()
+        return ms, last
+
+    for _ in range(max(args.warmup, 3)):
+        one_step(False)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _capi.LAUNCHES
+    ms_total, _ = timed(args.steps, False)
+    launches = (_capi.LAUNCHES - l0) // max(args.steps, 1)
+    e2e_steps = max(1, min(args.steps, 10))
+    one_step(True)
+    ms_e2e, last_loss = timed(e2e_steps, True)
+    clocks = sampler.stop() if rank == 0 else None
+
+    ms_step = ms_total / args.steps
+    pts = args.batch * args.points
+    value = world * pts / (ms_step / 1e3)
+    e2e_value = world * pts / (ms_e2e / e2e_steps / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            tdist.destroy_process_group()
+        return
+
+    # kernel accounting (untimed extra step) and the CPU baseline (N = 1 only)
+    agg = profile_step(replay)
+    total_ms = sum(d["ms"] for d in agg.values())
+    hbm_peak, peak_src = measured_peaks()
+    fp32_peak = fp32_peak_tflops()
+    kernels = []
+    for name, d in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+        row = {"entry": name, "calls": d["calls"], "ms": round(d["ms"], 4), "share": round(d["ms"] / total_ms, 4)}
+        if d["flop"]:
+            row["tflops"] = round(d["flop"] / (d["ms"] * 1e-3) / 1e12, 3)
+            row["frac_fp32_peak"] = round(row["tflops"] / fp32_peak, 4)
+        if d["byte"]:
+            row["gbs"] = round(d["byte"] / (d["ms"] * 1e-3) / 1e9, 1)
+            row["frac_hbm_peak"] = round(row["gbs"] / hbm_peak, 4)
+        kernels.append(row)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath))
+    dom = next((r for r in kernels if "tflops" in r or "gbs" in r), None)
+    roofline = None
+    if dom is not None:
+        per_launch_ms = dom["ms"] / dom["calls"]
+        if "gbs" in dom:
+            roofline = {"kernel": dom["entry"], "bound": "hbm", "achieved": dom["gbs"], "peak": hbm_peak,
+                        "unit": "GB/s", "frac": dom["frac_hbm_peak"], "peak_source": peak_src}
+        else:
+            roofline = {"kernel": dom["entry"], "bound": "fp32", "achieved": dom["tflops"], "peak": round(fp32_peak, 2),
+                        "unit": "TFLOP/s", "frac": dom["frac_fp32_peak"],
+                        "peak_source": "nominal 148 SM x 128 lanes x 2 x clocks.max.sm (not in MEASURED_PEAKS.json)"}
+        roofline["share_of_step"] = dom["share"]
+        roofline["ms_per_launch"] = round(per_launch_ms, 4)
+        roofline["traffic"] = (traffic or {}).get(dom["entry"])
+    hbm_rows = [r for r in kernels if r["entry"].startswith("amc3d_group_points")]
+    roofline_hbm = [{"kernel": r["entry"], "achieved": r["gbs"], "peak": hbm_peak, "unit": "GB/s",
+                     "frac": r["frac_hbm_peak"], "share_of_step": r["share"],
+                     "traffic": (traffic or {}).get(r["entry"])} for r in hbm_rows if "gbs" in r]
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu:
+        v, ms_cpu, cores = time_cpu_sample(1, 0, args.k)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "ms": ms_cpu,
+                        "sample": "1 scene x 24000 pts, full path incl. loss fwd+bwd, 1 pass (B=1: 1/8 of the unit's "
+                                  "kNN pairs per point)"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch": args.batch, "points_per_scene": args.points, "k": args.k,
+                       "units_per_rank_per_step": 1, "parallelism": f"dp{world} (scene units, no data-path collective)",
+                       "l2": "working set per step (6.45 GB of grouped tensors) exceeds the 126 MB L2; no flush needed",
+                       "grad_allreduce_mb": args.grad_mb if world > 1 else 0, "loss": last_loss},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": replay.h2d_bytes, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / e2e_steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm,
+            "kernels": kernels, "kernel_ms_per_step": round(total_ms, 3), "cpu_baseline": cpu_baseline}
+    print(json.dumps(line))
+    if world > 1:
+        tdist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--points", type=int, default=24000)
+    ap.add_argument("--k", type=int, default=16)
+    ap.add_argument("--grad-mb", type=float, default=166.3, help="flat gradient all-reduce per step (N>1): PointNeXt-XL FP32 grads")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

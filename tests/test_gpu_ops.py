@@ -1,4 +1,12 @@
-"""GPU parity of the point-grouping operators against the CPU restatement of the reference
+"""kNN tie note: the reference heap (knnquery_cuda_kernel.cu:21-48) is order- and membership-unstable
+under exactly equal distances; the sm_100a kernel returns the (d2, index)-lexicographic top-k
+("ties broken by lowest index", BASELINE.json north_star).  The two agree on every tie-free row.
+Random float32 ties do occur at scale (~k^2/2^24 per row), so: squared distances are compared
+bit-exactly against the literal-heap oracle on ALL rows (the sorted multiset is tie-independent),
+indices bit-exactly against the lexicographic oracle on all rows, and against the literal-heap
+oracle on the rows whose k+1 nearest distances are distinct.
+
+GPU parity of the point-grouping operators against the CPU restatement of the reference
 kernels (oracle/ops_oracle.c), called through the reference-facing Python operators, which in
 turn go through the C-ABI of include/amc3d.h.  Bar: bit-exact indices / distances / gathers;
 scatter-add gradients within 1e-5 relative (the reference's own atomics are order-dependent)."""
@@ -19,25 +27,37 @@ def _t(a):
 
 
 # ------------------------------------------------------------------ kNN
+def _check_knn(idx, dist, k, xyz, q, o, qo, sqrt):
+    hi, hd2 = oo.knnquery(k, xyz, q, o, qo)                 # literal reference heap
+    li, ld2 = oo.knnquery(k, xyz, q, o, qo, lex=True)       # (d2, index) lexicographic
+    exp = np.sqrt(hd2) if sqrt else hd2
+    assert np.array_equal(dist, exp)
+    assert np.array_equal(idx, li)
+    if k < 128:
+        _, d2p = oo.knnquery(k + 1, xyz, q, o, qo)
+        tie_free = (np.diff(d2p, axis=1) > 0).all(1) | (d2p[:, -1] >= 1e10)
+        tie_free &= (np.diff(hd2, axis=1) > 0).all(1) | (hd2[:, -1] >= 1e10)
+        assert tie_free.mean() > 0.98
+        assert np.array_equal(idx[tie_free], hi[tie_free])
+
+
 @pytest.mark.parametrize("k", [1, 3, 4, 8, 12, 16, 24, 32, 33, 64, 100])
 def test_knn_single_segment(k):
     from amcontrast3d_b200 import pointops
     xyz, _ = scenes.surface_scene(6000, seed=3)
     o = np.array([6000], dtype=np.int32)
-    ri, rd2 = oo.knnquery(k, xyz, None, o, o)
     idx, dist = pointops.knnquery(k, _t(xyz), None, _t(o), _t(o))
     assert idx.dtype == torch.int32 and dist.dtype == torch.float32
-    assert np.array_equal(idx.cpu().numpy(), ri)
-    assert np.array_equal(dist.cpu().numpy(), np.sqrt(rd2))
+    _check_knn(idx.cpu().numpy(), dist.cpu().numpy(), k, xyz, xyz, o, o, sqrt=True)
 
 
 def test_knn_raw_dist2_bit_exact_and_nsample_tensor():
     from amcontrast3d_b200 import _amloss, pointops
     xyz, _ = scenes.volume_scene(5000, seed=5)
     o = np.array([5000], dtype=np.int32)
-    ri, rd2 = oo.knnquery(16, xyz, None, o, o)
+    ri, rd2 = oo.knnquery(16, xyz, None, o, o, lex=True)
     idx, d2 = _amloss.knn_raw(16, _t(xyz), None, _t(o), _t(o))
-    assert np.array_equal(idx.cpu().numpy(), ri) and np.array_equal(d2.cpu().numpy(), rd2)
+    _check_knn(idx.cpu().numpy(), d2.cpu().numpy(), 16, xyz, xyz, o, o, sqrt=False)
     # nsample as a 0-dim tensor (AEF/utils.py:29 passes torch.prod(...))
     idx2, _ = pointops.knnquery(torch.prod(torch.tensor([4, 4])), _t(xyz), _t(xyz), _t(o), _t(o))
     assert np.array_equal(idx2.cpu().numpy(), ri)
@@ -53,7 +73,7 @@ def test_knn_ragged_segments_and_cross_sets():
     o = np.cumsum(sizes).astype(np.int32)
     qo = np.cumsum(qsizes).astype(np.int32)
     for k in (8, 16, 40):
-        ri, rd2 = oo.knnquery(k, xyz, q, o, qo)
+        ri, rd2 = oo.knnquery(k, xyz, q, o, qo, lex=True)
         idx, dist = pointops.knnquery(k, _t(xyz), _t(q), _t(o), _t(qo))
         assert np.array_equal(idx.cpu().numpy(), ri)
         assert np.array_equal(dist.cpu().numpy(), np.sqrt(rd2))
@@ -66,9 +86,8 @@ def test_knn_label_vote_shape():
     for kr, m in ((4, 2048), (16, 512), (64, 128)):
         q = np.ascontiguousarray(xyz[:m])
         o, qo = np.array([8192], dtype=np.int32), np.array([m], dtype=np.int32)
-        ri, rd2 = oo.knnquery(kr, xyz, q, o, qo)
         idx, dist = pointops.knnquery(kr, _t(xyz), _t(q), _t(o), _t(qo))
-        assert np.array_equal(idx.cpu().numpy(), ri)
+        _check_knn(idx.cpu().numpy(), dist.cpu().numpy(), kr, xyz, q, o, qo, sqrt=True)
 
 
 def test_knn_empty_and_errors():
@@ -96,12 +115,8 @@ def test_knn_full_size_properties():
     assert (np.diff(d2, axis=1) >= 0).all()
     assert (d2[:, 0] == 0).all()
     sample = np.random.default_rng(0).choice(n, 1024, replace=False)
-    ri, rd2 = oo.knnquery(16, flat, np.ascontiguousarray(flat[sample]), o, np.array([1024], dtype=np.int32))
-    assert np.array_equal(d2[sample], rd2)
-    # overlapping scenes may contain exact distance ties; compare indices where the row is tie-free
-    tie_free = (np.diff(rd2, axis=1) > 0).all(1)
-    assert tie_free.mean() > 0.9
-    assert np.array_equal(idx[sample][tie_free], ri[tie_free])
+    _check_knn(idx[sample], d2[sample], 16, flat, np.ascontiguousarray(flat[sample]), o,
+               np.array([1024], dtype=np.int32), sqrt=False)
 
 
 # ------------------------------------------------------------------ FPS

@@ -22,10 +22,11 @@ def test_knn_vs_reference_kernel():
     o = _t(np.array([24000], dtype=np.int32))
     for k in (4, 16, 24, 32, 64):
         ri, rd = rk.knnquery(k, flat, flat, o, o)
+        _, rdp = rk.knnquery(k + 1, flat, flat, o, o)
         i, d = _amloss.knn_raw(k, flat, flat, o, o)
-        assert torch.equal(d, rd)
-        tie_free = (rd[:, 1:] > rd[:, :-1]).all(1)
-        assert tie_free.float().mean() > 0.99
+        assert torch.equal(d, rd)                            # sorted distances: identical on every row
+        tie_free = (rdp[:, 1:] > rdp[:, :-1]).all(1)         # rows whose k+1 nearest distances are distinct
+        assert tie_free.float().mean() > 0.98
         assert torch.equal(i[tie_free], ri[tie_free])
 
 
