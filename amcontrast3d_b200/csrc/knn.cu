@@ -18,6 +18,7 @@
 //     bank-conflict-free shared-memory column instead.
 // FP32-pipe bound: 6 FP32 instructions + ~1.3 compare/select per pair.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace amc3d {
 
@@ -251,9 +252,22 @@ static void launch_reg(bool check, int blocks, cudaStream_t st, int n, int m, in
                                                                       offset, new_offset, idx, dist2);
 }
 
+int knn_grid_single_segment(int n, int m, int nsample, const float *xyz, const float *new_xyz, int *idx,
+                            float *dist2, cudaStream_t st);   // knn_grid.cu
+
 }  // namespace amc3d
 
 using namespace amc3d;
+
+// AMC3D_KNN_BRUTE=1 forces the brute-force kernels (used to measure them; results are identical)
+static bool force_brute() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("AMC3D_KNN_BRUTE");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
 
 extern "C" int amc3d_knnquery(int n, int m, int nseg, int nsample, const float *xyz,
                               const float *new_xyz, const int *offset, const int *new_offset,
@@ -263,6 +277,16 @@ extern "C" int amc3d_knnquery(int n, int m, int nseg, int nsample, const float *
     AMC3D_REQUIRE(nsample <= 128, AMC3D_ELIMIT, "knnquery: nsample=%d > 128", nsample);
     if (m == 0) return 0;
     cudaStream_t st = as_stream(stream);
+    // One segment (offset = [n], new_offset = [m] — what AMContrast3D always passes): exact search with
+    // spatial culling.  Small problems are not worth the sort.
+    if (nseg == 1 && n >= 2048 && !force_brute()) {
+        const int rc = knn_grid_single_segment(n, m, nsample, xyz, new_xyz, idx, dist2, st);
+        if (rc != 0) {
+            set_error("knnquery (grid): %s", cudaGetErrorString((cudaError_t)rc));
+            return rc;
+        }
+        return check_launch("knnquery");
+    }
     // A single segment (the AMContrast3D case: offset = [B*n]) never needs the per-candidate
     // range check; with several segments a CTA may straddle a boundary, so check.
     const bool check = nseg > 1;
