@@ -124,12 +124,19 @@ def _kernels_in(name: str, args) -> int:
     return 1
 
 
+_FN = {}
+
+
 def call(name: str, *args) -> None:
     """Invoke an int-returning entry point and raise on a non-zero code."""
     global LAUNCHES
-    fn = getattr(load(), name)
+    fn = _FN.get(name)
+    if fn is None:
+        fn = _FN[name] = getattr(load(), name)
     if PROFILE is None:
-        check(fn(*args), name)
+        rc = fn(*args)
+        if rc != 0:
+            check(rc, name)
     else:
         import torch
 
@@ -162,10 +169,24 @@ _NO_CPU = ("amc3d kernels need CUDA tensors: there is no CPU path in this packag
            "(the CPU restatement lives in oracle/ and is test infrastructure only)")
 
 
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
 def guard(t):
-    """Device guard for the launch; refuses CPU tensors loudly."""
+    """Device guard for the launch; refuses CPU tensors loudly.  Switching devices is only needed
+    when the tensor does not live on the current one (never, with one process per GPU)."""
     import torch
 
     if not t.is_cuda:
         raise Amc3dError(_NO_CPU)
+    if t.device.index == torch.cuda.current_device():
+        return _NO_GUARD
     return torch.cuda.device(t.device)

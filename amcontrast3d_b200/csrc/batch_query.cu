@@ -7,6 +7,7 @@
 // (one broadcast LDS.128 per 1.33 points), 256 queries per CTA.  Distances are the
 // reference expression bit for bit (common.cuh dist2_ref, operand order new - support).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace amc3d {
 
@@ -147,6 +148,23 @@ three_nn_kernel(int n, int m, const float *__restrict__ unknown, const float *__
     }
 }
 
+// knn_grid.cu: the same searches with spatial culling (identical results)
+int knn_grid_batched(int nb, int n, int m, int nsample, const float *xyz, const float *new_xyz, int *idx,
+                     float *dist2, cudaStream_t st);
+int ball_grid_batched(int nb, int n, int m, float radius, int nsample, const float *xyz, const float *new_xyz,
+                      int *idx, cudaStream_t st);
+
+// support points per cloud from which the culled search pays for its sort (AMC3D_GRID_MIN overrides;
+// 0 disables the culled path)
+static int grid_min() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("AMC3D_GRID_MIN");
+        v = e ? atoi(e) : 2048;
+    }
+    return v;
+}
+
 }  // namespace amc3d
 
 using namespace amc3d;
@@ -157,6 +175,14 @@ extern "C" int amc3d_ball_query(int b, int n, int m, float radius, int nsample,
                   "ball_query: bad sizes b=%d n=%d m=%d nsample=%d", b, n, m, nsample);
     AMC3D_REQUIRE(b <= 65535, AMC3D_ELIMIT, "ball_query: batch %d > 65535", b);
     if (b == 0 || m == 0 || n == 0) return 0;
+    if (grid_min() > 0 && n >= grid_min() && nsample <= 128) {
+        const int rc = ball_grid_batched(b, n, m, radius, nsample, xyz, new_xyz, idx, as_stream(stream));
+        if (rc != 0) {
+            set_error("ball_query (grid): %s", cudaGetErrorString((cudaError_t)rc));
+            return rc;
+        }
+        return check_launch("ball_query");
+    }
     dim3 grid(div_up(m, BQ_THREADS), b);
     ball_query_kernel<<<grid, BQ_THREADS, 0, as_stream(stream)>>>(n, m, radius, nsample, new_xyz, xyz, idx);
     return check_launch("ball_query");
@@ -167,6 +193,15 @@ extern "C" int amc3d_three_nn(int b, int n, int m, const float *unknown, const f
     AMC3D_REQUIRE(b >= 0 && n >= 0 && m >= 0, AMC3D_EINVAL, "three_nn: bad sizes b=%d n=%d m=%d", b, n, m);
     AMC3D_REQUIRE(b <= 65535, AMC3D_ELIMIT, "three_nn: batch %d > 65535", b);
     if (b == 0 || n == 0) return 0;
+    if (grid_min() > 0 && m >= grid_min()) {
+        // three_nn == exact 3-NN ordered by (d2, index): support = known, queries = unknown
+        const int rc = knn_grid_batched(b, m, n, 3, known, unknown, idx, dist2, as_stream(stream));
+        if (rc != 0) {
+            set_error("three_nn (grid): %s", cudaGetErrorString((cudaError_t)rc));
+            return rc;
+        }
+        return check_launch("three_nn");
+    }
     dim3 grid(div_up(n, BQ_THREADS), b);
     three_nn_kernel<<<grid, BQ_THREADS, 0, as_stream(stream)>>>(n, m, unknown, known, dist2, idx);
     return check_launch("three_nn");

@@ -25,11 +25,9 @@
 //     equal maxima falls back to an exact scan, so the index sequence is identical even on
 //     lattice inputs.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace amc3d {
-
-constexpr int FPS_WARPS = 4;
-constexpr int FPS_THREADS = FPS_WARPS * 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -53,6 +51,11 @@ __device__ __forceinline__ void st_async_v4(uint32_t raddr, uint32_t rbar, uint3
                  ::"r"(raddr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(rbar)
                  : "memory");
 }
+__device__ __forceinline__ void st_async_b32(uint32_t raddr, uint32_t rbar, uint32_t a) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                 ::"r"(raddr), "r"(a), "r"(rbar)
+                 : "memory");
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -63,37 +66,89 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
         "@!p bra WAIT_LOOP;\n\t}" ::"r"(bar), "r"(parity)
         : "memory");
 }
+// shared-memory accesses through 32-bit shared addresses computed once outside the round loop
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a) : "memory");
+    return r;
+}
+__device__ __forceinline__ uint32_t lds_b32(uint32_t a) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a) : "memory");
+    return r;
+}
+__device__ __forceinline__ void sts_v4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void sts_b32(uint32_t a, uint32_t x) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(x) : "memory");
+}
 
-// tie key: lower wins.  (bit-reversed (k mod bs)) << 22 | (k div bs)
+// opaque register copy: the value can no longer be rematerialised from its defining expression
+__device__ __forceinline__ uint32_t pin(uint32_t v) {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+
+// tie key: lower wins.  (bit-reversed (k mod bs)) << 22 | (k div bs);  k < 0 (no valid point) never wins
 __device__ __forceinline__ uint32_t tie_key(int k, int log2bs) {
+    if (k < 0) return 0xffffffffu;
     const uint32_t low = (uint32_t)k & ((1u << log2bs) - 1u);
     const uint32_t rev = log2bs == 0 ? 0u : (__brev(low) >> (32 - log2bs));
     return (rev << 22) | ((uint32_t)k >> log2bs);
 }
 
-struct __align__(16) FpsCand {
-    uint32_t v;    // running distance bits (non-negative float: bit order == value order)
-    uint32_t tb;   // tie key
-    float x, y, z; // coordinates of the candidate (next round's reference point)
-    int k;         // its index
-    uint32_t pad0, pad1;
-};
-static_assert(sizeof(FpsCand) == 32, "FpsCand must be 32 bytes");
+// A candidate is 20 bytes in a 32-byte slot: {value bits, index, x, y} {z}.  The value is a
+// non-negative float, so its bit pattern orders like the value.
+constexpr int CAND_BYTES = 32;
+constexpr int CAND_TX = 20;      // bytes actually transferred per candidate
 
-template <int CS, int PPT>
-__global__ void __launch_bounds__(FPS_THREADS)
+// argmax over the candidates held one per lane (lanes >= count hold v = 0, k = -1): returns the
+// lane of the winner.  The tie key is only evaluated when two candidates share the maximum.
+__device__ __forceinline__ int cand_argmax(uint32_t v, int k, int log2bs) {
+    const uint32_t gv = __reduce_max_sync(0xffffffffu, v);
+    const uint32_t gb = __ballot_sync(0xffffffffu, v == gv);
+    if ((gb & (gb - 1)) == 0) return __ffs(gb) - 1;
+    const uint32_t tb = v == gv ? tie_key(k, log2bs) : 0xffffffffu;
+    const uint32_t gt = __reduce_min_sync(0xffffffffu, tb);
+    return __ffs(__ballot_sync(0xffffffffu, v == gv && tb == gt)) - 1;
+}
+
+template <int N>
+__device__ __forceinline__ float tree_max(const float (&t)[N]) {
+    float a[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) a[i] = t[i];
+#pragma unroll
+    for (int w = N; w > 1; w = (w + 1) / 2) {
+#pragma unroll
+        for (int i = 0; i < w / 2; ++i) a[i] = fmaxf(a[i], a[w - 1 - i]);
+    }
+    return a[0];
+}
+
+// One round costs one dependent chain; everything below is arranged to keep that chain short
+// (profiles/r01_fps_before.md: 1970 cycles/round, of which the exchange itself was ~450):
+//   * the per-thread maximum is a tree, the slot holding it is recovered afterwards from a
+//     bit mask of independent compares (no serial compare/select chain over the PPT slots);
+//   * tie keys are evaluated only when two maxima are bit-equal (never, on real scenes);
+//   * shared-memory addresses are plain 32-bit registers computed before the loop.
+template <int CS, int PPT, int NW>
+__global__ void __launch_bounds__(NW * 32)
 fps_cluster_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, float *__restrict__ temp,
                    int *__restrict__ idxs) {
-    extern __shared__ float4 s_pts[];                // [PPT][FPS_THREADS] copy of this CTA's points
-    __shared__ FpsCand s_warp[2][FPS_WARPS];         // per-warp candidates (double-buffered for CS == 1)
-    __shared__ FpsCand s_exch[2][CS];                // per-CTA candidates of the whole cluster
+    constexpr int NT = NW * 32;
+    extern __shared__ float4 s_pts[];                              // [PPT][NT] copy of this CTA's points
+    __shared__ __align__(16) unsigned char s_warp[2][NW][CAND_BYTES];   // per-warp candidates
+    __shared__ __align__(16) unsigned char s_exch[2][CS][CAND_BYTES];   // per-CTA candidates of the cluster
     __shared__ __align__(8) uint64_t s_bar[2];
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = (int)pin(threadIdx.x), lane = tid & 31, warp = tid >> 5;
     const int rank = (int)cluster_ctarank();
     const int batch = blockIdx.x / CS;
     xyz += 3ll * batch * n;
@@ -104,28 +159,36 @@ fps_cluster_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, floa
     const int base = rank * chunk;
 
     float x[PPT], y[PPT], z[PPT], t[PPT];
+    bool any_valid = false;
 #pragma unroll
     for (int s = 0; s < PPT; ++s) {
-        const int l = s * FPS_THREADS + tid;
+        const int l = s * NT + tid;
         const int k = base + l;
         if (l < chunk && k < n) {
             x[s] = __ldg(xyz + 3ll * k);
             y[s] = __ldg(xyz + 3ll * k + 1);
             z[s] = __ldg(xyz + 3ll * k + 2);
             t[s] = temp[k];
+            any_valid = true;
         } else {
             // +inf coordinates give d = +inf and fminf(inf, 0) = 0: a padding slot stays at
             // distance 0 and is excluded from tie resolution below
             x[s] = y[s] = z[s] = INFINITY;
             t[s] = 0.f;
         }
-        s_pts[s * FPS_THREADS + tid] = make_float4(x[s], y[s], z[s], 0.f);
+        s_pts[s * NT + tid] = make_float4(x[s], y[s], z[s], 0.f);
     }
+    const bool warp_valid = __any_sync(0xffffffffu, any_valid);
 
     if (tid == 0) {
         mbar_init(smem_u32(&s_bar[0]), 1);
         mbar_init(smem_u32(&s_bar[1]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // a warp without a single valid point publishes a losing candidate once and only keeps the barriers
+    if (lane == 0) {
+        sts_v4(smem_u32(&s_warp[0][warp][0]), 0u, 0xffffffffu, 0u, 0u);
+        sts_v4(smem_u32(&s_warp[1][warp][0]), 0u, 0xffffffffu, 0u, 0u);
     }
     __syncthreads();
     cluster_sync_all();
@@ -133,106 +196,114 @@ fps_cluster_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, floa
     float x1 = __ldg(xyz), y1 = __ldg(xyz + 1), z1 = __ldg(xyz + 2);
     if (rank == 0 && tid == 0) idxs[0] = 0;
 
+    // addresses used every round, pinned in registers: without the opaque moves ptxas re-derives the
+    // shared window base (S2UR SR_CgaCtaId + ULEA, ~30 cycles of scoreboard wait each) at every use
+    const uint32_t a_pts = pin(smem_u32(&s_pts[tid]));
+    const uint32_t a_warp0 = pin(smem_u32(&s_warp[0][0][0]));      // + par*NW*32 + w*32
+    const uint32_t a_exch0 = pin(smem_u32(&s_exch[0][0][0]));      // + par*CS*32 + r*32
+    const uint32_t lbar0 = pin(smem_u32(&s_bar[0])), lbar1 = pin(smem_u32(&s_bar[1]));
     // warp 0, lane r delivers this CTA's candidate to CTA r of the cluster
     const uint32_t peer = lane < CS ? lane : 0;
-    const uint32_t dst0 = mapa_u32(smem_u32(&s_exch[0][rank]), peer);
-    const uint32_t dst1 = mapa_u32(smem_u32(&s_exch[1][rank]), peer);
-    const uint32_t rbar0 = mapa_u32(smem_u32(&s_bar[0]), peer);
-    const uint32_t rbar1 = mapa_u32(smem_u32(&s_bar[1]), peer);
-    const uint32_t lbar0 = smem_u32(&s_bar[0]), lbar1 = smem_u32(&s_bar[1]);
+    const uint32_t dst0 = mapa_u32(a_exch0 + rank * CAND_BYTES, peer);
+    const uint32_t dst1 = mapa_u32(a_exch0 + (CS + rank) * CAND_BYTES, peer);
+    const uint32_t rbar0 = mapa_u32(lbar0, peer), rbar1 = mapa_u32(lbar1, peer);
 
     uint32_t par = 0, phase = 0;
     for (int j = 1; j < m; ++j) {
-        // ---- running distance update; every thread tracks its first maximal slot -------------
-        float vmax = -1.f;
-        int bslot = 0;
+        // ---- running distance update ------------------------------------------------------------
 #pragma unroll
         for (int s = 0; s < PPT; ++s) {
             const float d = dist2_ref(x[s] - x1, y[s] - y1, z[s] - z1);
             t[s] = fminf(d, t[s]);
-            if (t[s] > vmax) { vmax = t[s]; bslot = s; }
         }
-        const uint32_t vb = __float_as_uint(vmax);
-        const uint32_t wv = __reduce_max_sync(0xffffffffu, vb);
-        const bool mine = vb == wv;
-        int neq = 0;
-        if (mine) {
+        const uint32_t my_warp_slot = a_warp0 + ((CS == 1 ? par * NW : 0) + warp) * CAND_BYTES;
+        if (warp_valid) {
+            const uint32_t vb = __float_as_uint(tree_max(t));
+            const uint32_t wv = __reduce_max_sync(0xffffffffu, vb);
+            const bool mine = vb == wv;
+            uint32_t smask = 0;                                   // slots of this thread equal to the warp maximum
 #pragma unroll
-            for (int s = 0; s < PPT; ++s) neq += __float_as_uint(t[s]) == wv ? 1 : 0;
-        }
-        const uint32_t bal = __ballot_sync(0xffffffffu, mine);
-        const uint32_t multi = __ballot_sync(0xffffffffu, mine && neq > 1);
-        int src = __ffs(bal) - 1;                        // the lane holding the warp's candidate
-        uint32_t mytb = 0xffffffffu;
-        if (multi != 0 || (bal & (bal - 1)) != 0) {
-            // exact tie resolution (rare): lowest tie key among all slots equal to the maximum
-            if (mine) {
+            for (int s = 0; s < PPT; ++s) smask |= (__float_as_uint(t[s]) == wv ? 1u : 0u) << s;
+            const uint32_t bal = __ballot_sync(0xffffffffu, mine);
+            const uint32_t multi = __ballot_sync(0xffffffffu, mine && (smask & (smask - 1)) != 0);
+            int src = __ffs(bal) - 1;                            // the lane holding the warp's candidate
+            int bslot = __ffs(smask) - 1;
+            if (multi != 0 || (bal & (bal - 1)) != 0) {
+                // exact tie resolution (rare): lowest tie key among all valid slots equal to the maximum
+                uint32_t mytb = 0xffffffffu;
+                if (mine) {
 #pragma unroll
-                for (int s = 0; s < PPT; ++s) {
-                    const int l = s * FPS_THREADS + tid;
-                    const bool valid = l < chunk && base + l < n;      // padding slots never win a tie
-                    const uint32_t tbs = valid ? tie_key(base + l, log2bs) : 0xffffffffu;
-                    if (__float_as_uint(t[s]) == wv && tbs < mytb) { mytb = tbs; bslot = s; }
+                    for (int s = 0; s < PPT; ++s) {
+                        const int l = s * NT + tid;
+                        const bool valid = l < chunk && base + l < n;      // padding slots never win a tie
+                        const uint32_t tbs = valid ? tie_key(base + l, log2bs) : 0xffffffffu;
+                        if (((smask >> s) & 1u) && tbs < mytb) { mytb = tbs; bslot = s; }
+                    }
+                }
+                const uint32_t wtb = __reduce_min_sync(0xffffffffu, mytb);
+                src = __ffs(__ballot_sync(0xffffffffu, mine && mytb == wtb)) - 1;
+                if (wtb == 0xffffffffu && lane == src) bslot = -1;          // only padding slots: losing candidate
+            }
+            // ---- the candidate lane publishes (value, index, xyz) for its warp ----------------
+            if (lane == src) {
+                if (bslot >= 0) {
+                    const uint4 cp = lds_v4(a_pts + bslot * (NT * 16));
+                    sts_v4(my_warp_slot, wv, (uint32_t)(base + bslot * NT + tid), cp.x, cp.y);
+                    sts_b32(my_warp_slot + 16, cp.z);
+                } else {
+                    sts_v4(my_warp_slot, 0u, 0xffffffffu, 0u, 0u);
                 }
             }
-            const uint32_t wtb = __reduce_min_sync(0xffffffffu, mytb);
-            src = __ffs(__ballot_sync(0xffffffffu, mine && mytb == wtb)) - 1;
-        } else if (mine) {
-            mytb = tie_key(base + bslot * FPS_THREADS + tid, log2bs);
         }
-        // ---- the candidate lane publishes (value, tie key, xyz, index) for its warp ------------
-        if (lane == src) {
-            const float4 cp = s_pts[bslot * FPS_THREADS + tid];
-            FpsCand c;
-            c.v = wv; c.tb = mytb; c.x = cp.x; c.y = cp.y; c.z = cp.z;
-            c.k = base + bslot * FPS_THREADS + tid; c.pad0 = 0; c.pad1 = 0;
-            s_warp[CS == 1 ? par : 0][warp] = c;
-        }
-        FpsCand c;
-        c.v = 0; c.tb = 0xffffffffu; c.x = c.y = c.z = 0.f; c.k = 0;
+        uint32_t cv = 0;
+        int ck = -1;
+        uint32_t a_cands;      // base of the candidate array every warp reduces below
         if (CS == 1) {
-            // single CTA: one barrier, then every warp reduces the 4 warp candidates itself
+            // single CTA: one barrier, then every warp reduces the NW warp candidates itself
             __syncthreads();
-            if (lane < FPS_WARPS) c = s_warp[par][lane];
+            a_cands = a_warp0 + par * NW * CAND_BYTES;
+            if (lane < NW) {
+                cv = lds_b32(a_cands + lane * CAND_BYTES);
+                ck = (int)lds_b32(a_cands + lane * CAND_BYTES + 4);
+            }
         } else {
-            // warps 1..3 only signal; warp 0 collects, reduces and pushes the CTA's candidate into
+            // warps 1.. only signal; warp 0 collects, picks the CTA's candidate and pushes it into
             // every CTA of the cluster (st.async completes a transaction on the receiver's mbarrier)
             const uint32_t lbar = par ? lbar1 : lbar0;
             if (warp != 0) {
-                asm volatile("bar.arrive 1, %0;" ::"r"(FPS_THREADS) : "memory");
+                asm volatile("bar.arrive 1, %0;" ::"r"(NT) : "memory");
             } else {
-                asm volatile("bar.sync 1, %0;" ::"r"(FPS_THREADS) : "memory");
-                if (lane == 0) mbar_expect_tx(lbar, CS * (uint32_t)sizeof(FpsCand));
-                FpsCand w;
-                w.v = 0; w.tb = 0xffffffffu; w.x = w.y = w.z = 0.f; w.k = 0;
-                if (lane < FPS_WARPS) w = s_warp[0][lane];
-                const uint32_t bv = __reduce_max_sync(0xffffffffu, w.v);
-                const uint32_t bt = __reduce_min_sync(0xffffffffu, w.v == bv ? w.tb : 0xffffffffu);
-                const int wl = __ffs(__ballot_sync(0xffffffffu, w.v == bv && w.tb == bt)) - 1;
-                const uint32_t w2 = __shfl_sync(0xffffffffu, __float_as_uint(w.x), wl);
-                const uint32_t w3 = __shfl_sync(0xffffffffu, __float_as_uint(w.y), wl);
-                const uint32_t w4 = __shfl_sync(0xffffffffu, __float_as_uint(w.z), wl);
-                const uint32_t w5 = __shfl_sync(0xffffffffu, (uint32_t)w.k, wl);
+                asm volatile("bar.sync 1, %0;" ::"r"(NT) : "memory");
+                if (lane == 0) mbar_expect_tx(lbar, CS * CAND_TX);
+                uint32_t wvv = 0;
+                int wk = -1;
+                if (lane < NW) {
+                    wvv = lds_b32(a_warp0 + lane * CAND_BYTES);
+                    wk = (int)lds_b32(a_warp0 + lane * CAND_BYTES + 4);
+                }
+                const int wl = cand_argmax(wvv, wk, log2bs);
                 if (lane < CS) {
+                    const uint4 w = lds_v4(a_warp0 + wl * CAND_BYTES);
+                    const uint32_t wz = lds_b32(a_warp0 + wl * CAND_BYTES + 16);
                     const uint32_t dst = par ? dst1 : dst0, rbar = par ? rbar1 : rbar0;
-                    st_async_v4(dst, rbar, bv, bt, w2, w3);
-                    st_async_v4(dst + 16, rbar, w4, w5, 0u, 0u);
+                    st_async_v4(dst, rbar, w.x, w.y, w.z, w.w);
+                    st_async_b32(dst + 16, rbar, wz);
                 }
             }
             mbar_wait(lbar, phase);
-            if (lane < CS) c = s_exch[par][lane];
+            a_cands = a_exch0 + par * CS * CAND_BYTES;
+            if (lane < CS) {
+                cv = lds_b32(a_cands + lane * CAND_BYTES);
+                ck = (int)lds_b32(a_cands + lane * CAND_BYTES + 4);
+            }
         }
-        // ---- every warp reduces the candidates (one per lane) with REDUX ------------------------
-        const uint32_t gv = __reduce_max_sync(0xffffffffu, c.v);
-        const uint32_t gt = __reduce_min_sync(0xffffffffu, c.v == gv ? c.tb : 0xffffffffu);
-        const int gl = __ffs(__ballot_sync(0xffffffffu, c.v == gv && c.tb == gt)) - 1;
-        x1 = __shfl_sync(0xffffffffu, c.x, gl);
-        y1 = __shfl_sync(0xffffffffu, c.y, gl);
-        z1 = __shfl_sync(0xffffffffu, c.z, gl);
-        if (rank == 0 && warp == 0) {
-            const int kwin = __shfl_sync(0xffffffffu, c.k, gl);
-            if (lane == 0) idxs[j] = kwin;
-        }
+        // ---- every warp finds the winner among the candidates and reads its coordinates ---------
+        const int gl = cand_argmax(cv, ck, log2bs);
+        const uint4 win = lds_v4(a_cands + gl * CAND_BYTES);
+        z1 = __uint_as_float(lds_b32(a_cands + gl * CAND_BYTES + 16));
+        x1 = __uint_as_float(win.z);
+        y1 = __uint_as_float(win.w);
+        if (rank == 0 && tid == 0) idxs[j] = (int)win.y;
         par ^= 1;
         if (par == 0) phase ^= 1;
     }
@@ -240,7 +311,7 @@ fps_cluster_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, floa
     // the reference leaves the final running distances in temp
 #pragma unroll
     for (int s = 0; s < PPT; ++s) {
-        const int l = s * FPS_THREADS + tid;
+        const int l = s * NT + tid;
         const int k = base + l;
         if (l < chunk && k < n) temp[k] = t[s];
     }
@@ -290,22 +361,23 @@ fps_global_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, float
     }
 }
 
-template <int CS, int PPT>
+template <int CS, int PPT, int NW>
 static cudaError_t launch_cluster(int b, int n, int m, int log2bs, const float *xyz, float *temp, int *idx,
                                   cudaStream_t st) {
-    const size_t smem = sizeof(float4) * PPT * FPS_THREADS;
+    const size_t smem = sizeof(float4) * PPT * NW * 32;
+    auto kern = fps_cluster_kernel<CS, PPT, NW>;
     cudaError_t e;
     if (smem > 40 * 1024) {
-        e = cudaFuncSetAttribute(fps_cluster_kernel<CS, PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     if (CS > 8) {
-        e = cudaFuncSetAttribute(fps_cluster_kernel<CS, PPT>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e != cudaSuccess) return e;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(b * CS);
-    cfg.blockDim = dim3(FPS_THREADS);
+    cfg.blockDim = dim3(NW * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -315,30 +387,48 @@ static cudaError_t launch_cluster(int b, int n, int m, int log2bs, const float *
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, fps_cluster_kernel<CS, PPT>, n, m, log2bs, xyz, temp, idx);
+    return cudaLaunchKernelEx(&cfg, kern, n, m, log2bs, xyz, temp, idx);
 }
 
-template <int CS>
-static cudaError_t launch_small(int ppt, int b, int n, int m, int log2bs, const float *xyz, float *temp, int *idx,
-                                cudaStream_t st) {
-    if (ppt <= 1) return launch_cluster<CS, 1>(b, n, m, log2bs, xyz, temp, idx, st);
-    if (ppt <= 2) return launch_cluster<CS, 2>(b, n, m, log2bs, xyz, temp, idx, st);
-    return launch_cluster<CS, 3>(b, n, m, log2bs, xyz, temp, idx, st);
-}
-
-template <int CS>
+#define FPS_ARGS b, n, m, log2bs, xyz, temp, idx, st
+template <int CS, int NW>
 static cudaError_t launch_for_ppt(int ppt, int b, int n, int m, int log2bs, const float *xyz, float *temp, int *idx,
                                   cudaStream_t st) {
-    if (ppt <= 1) return launch_cluster<CS, 1>(b, n, m, log2bs, xyz, temp, idx, st);
-    if (ppt <= 2) return launch_cluster<CS, 2>(b, n, m, log2bs, xyz, temp, idx, st);
-    if (ppt <= 3) return launch_cluster<CS, 3>(b, n, m, log2bs, xyz, temp, idx, st);
-    if (ppt <= 4) return launch_cluster<CS, 4>(b, n, m, log2bs, xyz, temp, idx, st);
-    if (ppt <= 6) return launch_cluster<CS, 6>(b, n, m, log2bs, xyz, temp, idx, st);
-    if (ppt <= 8) return launch_cluster<CS, 8>(b, n, m, log2bs, xyz, temp, idx, st);
-    if (ppt <= 12) return launch_cluster<CS, 12>(b, n, m, log2bs, xyz, temp, idx, st);
-    if (ppt <= 16) return launch_cluster<CS, 16>(b, n, m, log2bs, xyz, temp, idx, st);
-    if (ppt <= 24) return launch_cluster<CS, 24>(b, n, m, log2bs, xyz, temp, idx, st);
-    return launch_cluster<CS, 32>(b, n, m, log2bs, xyz, temp, idx, st);
+    if (ppt <= 1) return launch_cluster<CS, 1, NW>(FPS_ARGS);
+    if (ppt <= 2) return launch_cluster<CS, 2, NW>(FPS_ARGS);
+    if (ppt <= 3) return launch_cluster<CS, 3, NW>(FPS_ARGS);
+    if (ppt <= 4) return launch_cluster<CS, 4, NW>(FPS_ARGS);
+    if (ppt <= 6) return launch_cluster<CS, 6, NW>(FPS_ARGS);
+    if (ppt <= 8) return launch_cluster<CS, 8, NW>(FPS_ARGS);
+    if (ppt <= 12) return launch_cluster<CS, 12, NW>(FPS_ARGS);
+    if (ppt <= 16) return launch_cluster<CS, 16, NW>(FPS_ARGS);
+    if (NW <= 8) {     // 24+ points per thread only fit the register file with <= 256 threads
+        if (ppt <= 24) return launch_cluster<CS, 24, (NW <= 8 ? NW : 8)>(FPS_ARGS);
+        if (NW <= 4 && ppt <= 32) return launch_cluster<CS, 32, (NW <= 4 ? NW : 4)>(FPS_ARGS);
+    }
+    return cudaErrorInvalidConfiguration;
+}
+
+template <int CS>
+static cudaError_t launch_for_nw(int nw, int b, int n, int m, int log2bs, const float *xyz, float *temp, int *idx,
+                                 cudaStream_t st) {
+    const int ppt = div_up(div_up(n, CS), nw * 32);
+    if (nw == 4) return launch_for_ppt<CS, 4>(ppt, FPS_ARGS);
+    if (nw == 8) return launch_for_ppt<CS, 8>(ppt, FPS_ARGS);
+    return launch_for_ppt<CS, 16>(ppt, FPS_ARGS);
+}
+
+static cudaError_t launch_for_cs(int cs, int nw, int b, int n, int m, int log2bs, const float *xyz, float *temp,
+                                 int *idx, cudaStream_t st) {
+    if (cs == 16) return launch_for_nw<16>(nw, FPS_ARGS);
+    if (cs == 8) return launch_for_nw<8>(nw, FPS_ARGS);
+    if (cs == 4) return launch_for_nw<4>(nw, FPS_ARGS);
+    return launch_for_nw<1>(nw, FPS_ARGS);
+}
+
+static int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
 }
 
 }  // namespace amc3d
@@ -355,23 +445,18 @@ extern "C" int amc3d_furthest_point_sampling(int b, int n, int m, const float *x
     int log2bs = 0;
     while ((2 << log2bs) <= n && log2bs < 10) ++log2bs;
 
-    // cluster size: as many CTAs as pay off (each round costs one exchange regardless)
-    cudaError_t e = cudaErrorInvalidValue;
-    const int cs = n > 1536 ? 16 : (n > 384 ? 4 : 1);
-    const int ppt = div_up(div_up(n, cs), FPS_THREADS);
-    if (ppt <= 32) {
-        if (cs == 16) {
-            e = launch_for_ppt<16>(ppt, b, n, m, log2bs, xyz, temp, idx, st);
-            if (e != cudaSuccess) {            // non-portable cluster size refused: try 8 CTAs
-                cudaGetLastError();
-                const int ppt8 = div_up(div_up(n, 8), FPS_THREADS);
-                if (ppt8 <= 32) e = launch_for_ppt<8>(ppt8, b, n, m, log2bs, xyz, temp, idx, st);
-            }
-        } else if (cs == 4) {
-            e = launch_small<4>(ppt, b, n, m, log2bs, xyz, temp, idx, st);
-        } else {
-            e = launch_small<1>(ppt, b, n, m, log2bs, xyz, temp, idx, st);
-        }
+    // cluster size and warps per CTA: as much parallelism as pays off (each round costs one
+    // exchange regardless); AMC3D_FPS_CS / AMC3D_FPS_NW override the choice for experiments
+    static const int env_cs = env_int("AMC3D_FPS_CS", 0), env_nw = env_int("AMC3D_FPS_NW", 0);
+    int cs = n > 1536 ? 16 : (n > 384 ? 4 : 1);
+    int nw = 4;
+    while (nw < 16 && div_up(div_up(n, cs), nw * 32) > 16) nw *= 2;
+    if (env_cs == 1 || env_cs == 4 || env_cs == 8 || env_cs == 16) cs = env_cs;
+    if (env_nw == 4 || env_nw == 8 || env_nw == 16) nw = env_nw;
+    cudaError_t e = launch_for_cs(cs, nw, FPS_ARGS);
+    if (e != cudaSuccess && cs == 16) {        // non-portable cluster size refused: try 8 CTAs
+        cudaGetLastError();
+        e = launch_for_cs(8, 8, FPS_ARGS);
     }
     if (e != cudaSuccess) {                    // very large scenes (or clusters unavailable)
         cudaGetLastError();

@@ -24,6 +24,7 @@
 //   * without a workspace (NULL) or for C < 8 (the xyz grouping, C = 3) a direct kernel
 //     keeps idx in registers across channels.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace amc3d {
 
@@ -131,6 +132,192 @@ group_bwd_cl_kernel(int C, int N, int P, const float *__restrict__ grad_out, con
         atomicAdd(acc + (long long)ib.y * C, gb.y);
         atomicAdd(acc + (long long)ib.z * C, gb.z);
         atomicAdd(acc + (long long)ib.w * C, gb.w);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// TMA-staged variants: a CTA owns a tile of 32 channels x 256 positions held in shared memory.
+//
+// forward   lane = channel: every neighbour index is ONE coalesced 128-byte read of the (B,N,C)
+//           workspace (L2-resident); the lane's 4 consecutive positions go to its tile row with a
+//           conflict-free STS.128 (row stride 260 floats = 4 mod 32 banks); after a barrier the 32
+//           rows leave as 32 bulk-async (TMA) stores of 1 KB with an L2 evict-first policy, so the
+//           write stream neither occupies the LSU nor evicts the workspace from L2.
+// backward  32 bulk-async loads bring the 32 x 1 KB grad rows in (mbarrier complete_tx); the
+//           scatter-add is issued as red.global.add.v4.f32: a lane owns 4 consecutive channels of
+//           one position, a warp instruction adds 4 positions x 128 contiguous bytes into the
+//           (B,N,C) accumulator.  Tile rows are laid out at r*288 + 4*(r/4) floats so that the
+//           position-major scalar LDS of that mapping is bank-conflict free.
+// ---------------------------------------------------------------------------------------
+constexpr int TP = 256;          // positions per tile
+constexpr int TC = 32;           // channels per tile
+constexpr int FWD_LD = TP + 4;   // forward tile row stride (floats)
+constexpr int BWD_LD = TP + 32;  // backward tile row stride (floats); row r starts at r*BWD_LD + 4*(r>>2)
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_store(void *gdst, uint32_t ssrc, uint32_t bytes, uint64_t pol) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gdst),
+                 "r"(ssrc), "r"(bytes), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t sdst, const void *gsrc, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(sdst),
+        "l"(gsrc), "r"(bytes), "r"(bar), "l"(pol)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+group_fwd_tma_kernel(int C, int N, int P, const float *__restrict__ srcT, const int *__restrict__ idx,
+                     float *__restrict__ out) {
+    extern __shared__ __align__(128) float tile[];   // [TC][FWD_LD]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * TC;
+    const int p0 = blockIdx.x * TP;
+    const int npos = min(TP, P - p0);                 // multiple of 4 (host checks P % 4 == 0)
+    const int cc = min(c0 + lane, C - 1);
+    const float *src = srcT + (long long)b * N * C + cc;
+    const int *ip = idx + (long long)b * P + p0 + warp * 32;
+    const int wpos = min(32, npos - warp * 32);       // positions of this warp (may be <= 0)
+    float *trow = tile + lane * FWD_LD + warp * 32;
+    if (wpos == 32) {
+        // full warp tile: two batches of 16 independent gathers in flight per lane
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int4 ii[4];
+            float4 v[4];
+#pragma unroll
+            for (int o = 0; o < 4; ++o) ii[o] = __ldg(reinterpret_cast<const int4 *>(ip + h * 16 + o * 4));
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                v[o].x = __ldg(src + (long long)ii[o].x * C);
+                v[o].y = __ldg(src + (long long)ii[o].y * C);
+                v[o].z = __ldg(src + (long long)ii[o].z * C);
+                v[o].w = __ldg(src + (long long)ii[o].w * C);
+            }
+#pragma unroll
+            for (int o = 0; o < 4; ++o) *reinterpret_cast<float4 *>(trow + h * 16 + o * 4) = v[o];
+        }
+    } else {
+        for (int o = 0; o * 4 < wpos; ++o) {
+            const int4 ia = __ldg(reinterpret_cast<const int4 *>(ip + o * 4));
+            float4 v;
+            v.x = __ldg(src + (long long)ia.x * C);
+            v.y = __ldg(src + (long long)ia.y * C);
+            v.z = __ldg(src + (long long)ia.z * C);
+            v.w = __ldg(src + (long long)ia.w * C);
+            *reinterpret_cast<float4 *>(trow + o * 4) = v;
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy
+    __syncthreads();
+    if (warp == 0) {
+        if (c0 + lane < C) {
+            const uint64_t pol = l2_evict_first_policy();
+            bulk_store(out + ((long long)b * C + c0 + lane) * P + p0, smem_addr(tile + lane * FWD_LD),
+                       (uint32_t)npos * 4u, pol);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the reads
+    }
+}
+
+__device__ __forceinline__ void red_v4(float *p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// grad_out (B,C,P), idx (B,P) -> accT (B,N,C) +=.  V4: vector reductions (needs C % 4 == 0)
+template <bool V4>
+__global__ void __launch_bounds__(256)
+group_bwd_tma_kernel(int C, int N, int P, const float *__restrict__ grad_out, const int *__restrict__ idx,
+                     float *__restrict__ accT) {
+    extern __shared__ __align__(128) float tile[];   // rows at r*BWD_LD + 4*(r>>2)
+    __shared__ __align__(8) uint64_t bar;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * TC;
+    const int p0 = blockIdx.x * TP;
+    const int npos = min(TP, P - p0);
+    const int rows = min(TC, C - c0);
+    const uint32_t bar_a = smem_addr(&bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 0) {
+        if (lane == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a),
+                         "r"((uint32_t)(rows * npos * 4))
+                         : "memory");
+        __syncwarp();
+        if (lane < rows) {
+            const uint64_t pol = l2_evict_first_policy();
+            bulk_load(smem_addr(tile + lane * BWD_LD + 4 * (lane >> 2)),
+                      grad_out + ((long long)b * C + c0 + lane) * P + p0, (uint32_t)npos * 4u, bar_a, pol);
+        }
+    }
+    // idx of this warp's 32 positions, one per lane (overlaps the bulk loads)
+    const int wbase = warp * 32;
+    const int wpos = min(32, npos - wbase);
+    int my_idx = 0;
+    if (lane < wpos) my_idx = __ldg(idx + (long long)b * P + p0 + wbase + lane);
+    {
+        uint32_t ok = 0;
+        while (!ok) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok)
+                : "r"(bar_a)
+                : "memory");
+        }
+    }
+    float *acc = accT + (long long)b * N * C + c0;
+    if (V4) {
+        // lane -> (position j = lane/8 of a group of 4, channel quad q = lane%8)
+        const int j = lane >> 3, q = lane & 7;
+        const float *t0 = tile + (4 * q) * BWD_LD + 4 * q + wbase + j;
+        const bool cok = 4 * q < rows;                 // C % 4 == 0: whole quads only
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            const int pi = __shfl_sync(0xffffffffu, my_idx, o * 4 + j);
+            if (o * 4 + j < wpos && cok) {
+                const float g0 = t0[o * 4];
+                const float g1 = t0[o * 4 + BWD_LD];
+                const float g2 = t0[o * 4 + 2 * BWD_LD];
+                const float g3 = t0[o * 4 + 3 * BWD_LD];
+                red_v4(acc + (long long)pi * C + 4 * q, g0, g1, g2, g3);
+            }
+        }
+    } else {
+        const float *t0 = tile + lane * BWD_LD + 4 * (lane >> 2) + wbase;
+        const bool cok = lane < rows;
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            if (o * 4 < wpos) {
+                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (cok) g = *reinterpret_cast<const float4 *>(t0 + o * 4);
+                const int i0 = __shfl_sync(0xffffffffu, my_idx, o * 4);
+                const int i1 = __shfl_sync(0xffffffffu, my_idx, o * 4 + 1);
+                const int i2 = __shfl_sync(0xffffffffu, my_idx, o * 4 + 2);
+                const int i3 = __shfl_sync(0xffffffffu, my_idx, o * 4 + 3);
+                if (cok) {
+                    atomicAdd(acc + (long long)i0 * C + lane, g.x);
+                    atomicAdd(acc + (long long)i1 * C + lane, g.y);
+                    atomicAdd(acc + (long long)i2 * C + lane, g.z);
+                    atomicAdd(acc + (long long)i3 * C + lane, g.w);
+                }
+            }
+        }
     }
 }
 
@@ -256,6 +443,17 @@ static inline int pick_cchunk(int C, long long blocks_xy) {
 
 using namespace amc3d;
 
+// AMC3D_GROUP_IMPL: 0 = register-only kernels, 1 = TMA-staged (scalar reductions in the backward),
+// 2 = TMA-staged with vector reductions (default)
+static int group_impl() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("AMC3D_GROUP_IMPL");
+        v = e ? atoi(e) : 2;
+    }
+    return v;
+}
+
 static int group_common(bool fwd, int b, int c, int n, long long P, const float *src, const int *idx,
                         float *dst, float *workspace, cudaStream_t st, const char *what) {
     if (b == 0 || c == 0 || P == 0) return 0;
@@ -265,12 +463,22 @@ static int group_common(bool fwd, int b, int c, int n, long long P, const float 
                          ((reinterpret_cast<uintptr_t>(fwd ? dst : const_cast<float *>(src)) & 15) == 0);
     if (workspace != nullptr && c >= 8 && aligned && n > 0) {
         dim3 grid((unsigned)div_up_ll(P, GRP_WARPS * 32), div_up(c, 32), b);
+        const int impl = group_impl();
         if (fwd) {
             launch_transpose<false>(b, c, n, src, workspace, st);  // (B,C,N) -> (B,N,C)
-            group_fwd_cl_kernel<<<grid, GRP_WARPS * 32, 0, st>>>(c, n, (int)P, workspace, idx, dst);
+            if (impl >= 1)
+                group_fwd_tma_kernel<<<grid, 256, TC * FWD_LD * sizeof(float), st>>>(c, n, (int)P, workspace, idx, dst);
+            else
+                group_fwd_cl_kernel<<<grid, GRP_WARPS * 32, 0, st>>>(c, n, (int)P, workspace, idx, dst);
         } else {
             cudaMemsetAsync(workspace, 0, sizeof(float) * (size_t)b * n * c, st);
-            group_bwd_cl_kernel<<<grid, GRP_WARPS * 32, 0, st>>>(c, n, (int)P, src, idx, workspace);
+            const size_t smem = (TC * BWD_LD + 32) * sizeof(float);
+            if (impl >= 2 && c % 4 == 0)
+                group_bwd_tma_kernel<true><<<grid, 256, smem, st>>>(c, n, (int)P, src, idx, workspace);
+            else if (impl >= 1)
+                group_bwd_tma_kernel<false><<<grid, 256, smem, st>>>(c, n, (int)P, src, idx, workspace);
+            else
+                group_bwd_cl_kernel<<<grid, GRP_WARPS * 32, 0, st>>>(c, n, (int)P, src, idx, workspace);
             launch_transpose<true>(b, n, c, workspace, dst, st);   // (B,N,C) -> += (B,C,N)
         }
     } else {

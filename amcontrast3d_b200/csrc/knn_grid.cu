@@ -1,5 +1,9 @@
-// Exact kNN with spatial culling for the single-segment case (offset = [n]) — the case
-// AMContrast3D always produces (pointnext_AA.py:461 flattens the batch into one segment).
+// Exact neighbour search with spatial culling: kNN for the single-segment case (offset = [n]) —
+// the case AMContrast3D always produces (pointnext_AA.py:461 flattens the batch into one segment) —
+// and, over the same structure built per batch element, three_nn (k = 3) and ball_query on batched
+// (B,N,3) clouds.  Everything below is "batched": nb clouds of n points each, cloud b's sorted
+// points living at [b*npad, b*npad + n) with npad = n rounded up to a whole tile, so that a tile
+// never straddles two clouds.  kNN uses nb = 1.
 //
 // The brute-force kernel (knn.cu) evaluates all m*n pairs: 3.7e10 for the stage-0 self-kNN of
 // BASELINE config 2, ~12 ms at the FP32 issue limit.  The result, however, is fully determined
@@ -47,10 +51,12 @@ __device__ __forceinline__ float ord2f(uint32_t o) {
     return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
 }
 
-// bb[0..2] = min (ordered), bb[3..5] = max (ordered); caller initialises to 0xffffffff / 0
+// bb[b*8 + 0..2] = min (ordered), bb[b*8 + 3..5] = max (ordered); initialised to 0xffffffff / 0
 __global__ void __launch_bounds__(256)
 bbox_kernel(int n, const float *__restrict__ xyz, uint32_t *__restrict__ bb) {
     __shared__ float s_lo[3][8], s_hi[3][8];
+    xyz += 3ll * blockIdx.y * n;
+    bb += 8 * blockIdx.y;
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
 #pragma unroll
@@ -88,9 +94,9 @@ bbox_kernel(int n, const float *__restrict__ xyz, uint32_t *__restrict__ bb) {
     }
 }
 
-__global__ void bbox_init_kernel(uint32_t *bb) {
-    if (threadIdx.x < 3) bb[threadIdx.x] = 0xffffffffu;
-    else if (threadIdx.x < 6) bb[threadIdx.x] = 0u;
+__global__ void bbox_init_kernel(int nb, uint32_t *bb) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nb * 8) bb[i] = (i & 7) < 3 ? 0xffffffffu : 0u;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -123,9 +129,11 @@ __global__ void __launch_bounds__(256)
 cell_count_kernel(int n, const float *__restrict__ xyz, const uint32_t *__restrict__ bb, int bits,
                   uint32_t *__restrict__ cell, int *__restrict__ counts) {
     const int i = blockIdx.x * 256 + threadIdx.x;
+    const int b = blockIdx.y;
     if (i >= n) return;
-    const uint32_t c = cell_of(__ldg(xyz + 3ll * i), __ldg(xyz + 3ll * i + 1), __ldg(xyz + 3ll * i + 2), bb, bits);
-    cell[i] = c;
+    const float *p = xyz + 3ll * ((long long)b * n + i);
+    const uint32_t c = ((uint32_t)b << (3 * bits)) | cell_of(__ldg(p), __ldg(p + 1), __ldg(p + 2), bb + 8 * b, bits);
+    cell[(long long)b * n + i] = c;
     atomicAdd(counts + c, 1);
 }
 
@@ -210,31 +218,33 @@ scan_add_kernel(int cells, int *__restrict__ counts, const int *__restrict__ tot
         }
 }
 
-// scatter into cell order; `starts` is consumed as the running fill pointer of each cell
+// scatter into cell order; `starts` is consumed as the running fill pointer of each cell.  The scan runs over
+// the cells of all clouds, so cloud b starts at b*n; `pad` = npad - n shifts it to b*npad.
 __global__ void __launch_bounds__(256)
-scatter_kernel(int n, const float *__restrict__ xyz, const uint32_t *__restrict__ cell,
+scatter_kernel(int n, int pad, const float *__restrict__ xyz, const uint32_t *__restrict__ cell,
                int *__restrict__ starts, float4 *__restrict__ sorted) {
     const int i = blockIdx.x * 256 + threadIdx.x;
+    const int b = blockIdx.y;
     if (i >= n) return;
-    const int pos = atomicAdd(starts + cell[i], 1);
-    sorted[pos] = make_float4(__ldg(xyz + 3ll * i), __ldg(xyz + 3ll * i + 1), __ldg(xyz + 3ll * i + 2),
-                              __int_as_float(i));
+    const long long g = (long long)b * n + i;
+    const int pos = atomicAdd(starts + cell[g], 1) + b * pad;
+    sorted[pos] = make_float4(__ldg(xyz + 3 * g), __ldg(xyz + 3 * g + 1), __ldg(xyz + 3 * g + 2), __int_as_float(i));
 }
 
 // ---------------------------------------------------------------------------------------
 // 3. tile boxes: one warp per tile of GT sorted points
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-tile_aabb_kernel(int n, int ntiles, const float4 *__restrict__ sorted, float4 *__restrict__ tlo,
+tile_aabb_kernel(int n, int ntb, int ntiles, const float4 *__restrict__ sorted, float4 *__restrict__ tlo,
                  float4 *__restrict__ thi) {
     const int t = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (t >= ntiles) return;
+    const int lt = t % ntb;                       // tile within its cloud
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int j = lane; j < GT; j += 32) {
-        const int i = t * GT + j;
-        if (i < n) {
-            const float4 p = __ldg(sorted + i);
+        if (lt * GT + j < n) {
+            const float4 p = __ldg(sorted + (long long)t * GT + j);
             lo[0] = fminf(lo[0], p.x); hi[0] = fmaxf(hi[0], p.x);
             lo[1] = fminf(lo[1], p.y); hi[1] = fmaxf(hi[1], p.y);
             lo[2] = fminf(lo[2], p.z); hi[2] = fmaxf(hi[2], p.z);
@@ -337,34 +347,48 @@ __device__ __forceinline__ float warp_kth_of_128(const float (&dd)[4], int k) {
     return __uint_as_float(T);
 }
 
+// geometry of a batched, tile-aligned sorted point set
+struct Geom {
+    int nb;      // clouds
+    int n;       // points per cloud
+    int npad;    // n rounded up to whole tiles
+    int ntb;     // tiles per cloud
+    int ngb;     // tile groups per cloud
+    int bits;    // grid bits per axis
+};
+
 template <int E>
 __global__ void __launch_bounds__(WQ_WARPS * 32)
-knn_wq_kernel(int n, int m, int nsample, int ntiles, int ngroups, int self, int qpw, const float4 *__restrict__ sp,
+knn_wq_kernel(Geom gs, int m, int mpad, int nsample, int self, int qpw, const float4 *__restrict__ sp,
               const float4 *__restrict__ tlo, const float4 *__restrict__ thi, const float4 *__restrict__ glo,
               const float4 *__restrict__ ghi, const float4 *__restrict__ sq, const int *__restrict__ cell_start,
-              const uint32_t *__restrict__ bb, int bits, int *__restrict__ idx, float *__restrict__ dist2) {
+              const uint32_t *__restrict__ bb, int *__restrict__ idx, float *__restrict__ dist2) {
     const int lane = threadIdx.x & 31;
     const int wq0 = (blockIdx.x * WQ_WARPS + (threadIdx.x >> 5)) * qpw;
+    const int n = gs.n;
 
     for (int j = 0; j < qpw; ++j) {
         const int q = wq0 + j;
-        if (q >= m) return;                                   // warp-uniform
+        if (q >= gs.nb * mpad) return;                        // warp-uniform
+        const int b = q / mpad;
+        if (q - b * mpad >= m) continue;                      // padding slot of the query layout
         const float4 me = __ldg(sq + q);
         const float qx = me.x, qy = me.y, qz = me.z;
         WarpList<E> best;
         best.init(nsample, lane);
         float td = KG_INIT;
         int ti = 0x7fffffff;
+        const int tb0 = b * gs.ntb;                           // first tile of the query's cloud
 
-        // evaluate the 128 points of tile t against this query; first=true seeds the list
+        // evaluate the 128 points of global tile t against this query; first=true seeds the list
         auto process_tile = [&](int t, bool first) {
             float dd[4];
             int oi[4];
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                const int s = t * GT + r * 32 + lane;
-                if (s < n) {
-                    const float4 p = __ldg(sp + s);
+                const int l = (t - tb0) * GT + r * 32 + lane;  // position within the cloud
+                if (l < n) {
+                    const float4 p = __ldg(sp + (long long)t * GT + r * 32 + lane);
                     dd[r] = dist2_ref(qx - p.x, qy - p.y, qz - p.z);
                     oi[r] = __float_as_int(p.w);
                 } else {
@@ -382,16 +406,16 @@ knn_wq_kernel(int n, int m, int nsample, int ntiles, int ngroups, int self, int 
                 bool cand = dd[r] <= td && lex_lt(dd[r], oi[r], td, ti);
                 uint32_t mask = __ballot_sync(0xffffffffu, cand);
                 while (mask) {
-                    const int b = __ffs(mask) - 1;
-                    const float cd = __shfl_sync(0xffffffffu, dd[r], b);
-                    const int ci = __shfl_sync(0xffffffffu, oi[r], b);
+                    const int bl = __ffs(mask) - 1;
+                    const float cd = __shfl_sync(0xffffffffu, dd[r], bl);
+                    const int ci = __shfl_sync(0xffffffffu, oi[r], bl);
                     best.insert(cd, ci, lane);
                     float nd;
                     int ni;
                     best.threshold(nd, ni);
                     // while seeding, the provisional (T, INT_MAX) bound stays until the list is full
                     if (!first || nd < KG_INIT) { td = nd; ti = ni; }
-                    cand = cand && lane != b && lex_lt(dd[r], oi[r], td, ti);
+                    cand = cand && lane != bl && lex_lt(dd[r], oi[r], td, ti);
                     mask = __ballot_sync(0xffffffffu, cand);
                 }
             }
@@ -401,63 +425,193 @@ knn_wq_kernel(int n, int m, int nsample, int ntiles, int ngroups, int self, int 
         // ---- the tile at the query's own position and its two neighbours first -------------
         int t0;
         if (self) t0 = q / GT;
-        else t0 = __ldg(cell_start + cell_of(qx, qy, qz, bb, bits)) / GT;
-        t0 = min(max(t0, 0), ntiles - 1);
-        const int r_lo = max(t0 - 1, 0), r_hi = min(t0 + 1, ntiles - 1);
+        else
+            t0 = (__ldg(cell_start + (((uint32_t)b << (3 * gs.bits)) | cell_of(qx, qy, qz, bb + 8 * b, gs.bits))) +
+                  b * (gs.npad - n)) / GT;
+        t0 = min(max(t0, tb0), tb0 + gs.ntb - 1);
+        const int r_lo = max(t0 - 1, tb0), r_hi = min(t0 + 1, tb0 + gs.ntb - 1);
         process_tile(t0, true);
         for (int t = r_lo; t <= r_hi; ++t)
             if (t != t0) process_tile(t, false);
 
         // ---- everything else through two levels of boxes -----------------------------------
-        for (int g0 = 0; g0 < ngroups; g0 += 32) {
+        for (int g0 = 0; g0 < gs.ngb; g0 += 32) {
             const int g = g0 + lane;
-            bool gs = false;
-            if (g < ngroups) gs = !(point_box2(qx, qy, qz, __ldg(glo + g), __ldg(ghi + g)) * KG_SAFE > td);
-            uint32_t gmask = __ballot_sync(0xffffffffu, gs);
+            bool gsel = false;
+            if (g < gs.ngb)
+                gsel = !(point_box2(qx, qy, qz, __ldg(glo + b * gs.ngb + g), __ldg(ghi + b * gs.ngb + g)) * KG_SAFE > td);
+            uint32_t gmask = __ballot_sync(0xffffffffu, gsel);
             while (gmask) {
                 const int gb = __ffs(gmask) - 1;
                 gmask &= gmask - 1;
-                const int t = (g0 + gb) * TG + lane;
+                const int lt = (g0 + gb) * TG + lane;            // tile within the cloud
+                const int t = tb0 + lt;
                 float lb = INFINITY;
-                if (t < ntiles && (t < r_lo || t > r_hi)) lb = point_box2(qx, qy, qz, __ldg(tlo + t), __ldg(thi + t));
+                if (lt < gs.ntb && (t < r_lo || t > r_hi)) lb = point_box2(qx, qy, qz, __ldg(tlo + t), __ldg(thi + t));
                 uint32_t tmask = __ballot_sync(0xffffffffu, !(lb * KG_SAFE > td));
                 while (tmask) {
-                    const int tb = __ffs(tmask) - 1;
+                    const int tbit = __ffs(tmask) - 1;
                     tmask &= tmask - 1;
-                    const float lbt = __shfl_sync(0xffffffffu, lb, tb);
+                    const float lbt = __shfl_sync(0xffffffffu, lb, tbit);
                     if (lbt * KG_SAFE > td) continue;              // threshold tightened meanwhile
-                    process_tile((g0 + gb) * TG + tb, false);
+                    process_tile(tb0 + (g0 + gb) * TG + tbit, false);
                 }
             }
         }
 
         // ---- write the live entries (slots S-nsample .. S-1) to the query's original row ----
-        const int qorig = __float_as_int(me.w);
+        const long long qorig = (long long)b * m + __float_as_int(me.w);
         const int shift = 32 * E - nsample;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const int s = lane * E + e - shift;
             if (s >= 0) {
-                idx[(long long)qorig * nsample + s] = best.i[e];
-                dist2[(long long)qorig * nsample + s] = best.d[e];
+                idx[qorig * nsample + s] = best.i[e];
+                dist2[qorig * nsample + s] = best.d[e];
             }
         }
     }
 }
 
-// boxes of TG consecutive tile boxes
+// ---------------------------------------------------------------------------------------
+// ball query over the same structure: the nsample SMALLEST original indices with d2 < r^2
+// ---------------------------------------------------------------------------------------
+// The reference scans the support cloud in index order and keeps the first nsample hits
+// (ball_query_gpu.cu:29-50), i.e. the nsample smallest indices inside the ball; slots beyond the hit
+// count repeat the first hit, rows without a hit are not written.  Here a warp visits only the
+// tiles whose box intersects the ball (conservatively: skipped only if lb2 * (1 - 2^-13) >= r^2) and
+// keeps the sorted list of the nsample smallest hit indices distributed over its lanes.
+template <int E>
+struct WarpIdxList {
+    int i[E];
+    __device__ __forceinline__ void init(int nsample, int lane) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) i[e] = (lane * E + e) < 32 * E - nsample ? -1 : 0x7fffffff;
+    }
+    __device__ __forceinline__ int threshold() const { return __shfl_sync(0xffffffffu, i[E - 1], 31); }
+    // insert ci, known to be smaller than the current last entry; warp-uniform argument
+    __device__ __forceinline__ void insert(int ci, int lane) {
+        bool lt[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) lt[e] = ci < i[e];
+        const int pi = __shfl_up_sync(0xffffffffu, i[E - 1], 1);
+        const bool plt = __shfl_up_sync(0xffffffffu, (int)lt[E - 1], 1) && lane > 0;
+#pragma unroll
+        for (int e = E - 1; e > 0; --e) i[e] = lt[e - 1] ? i[e - 1] : (lt[e] ? ci : i[e]);
+        i[0] = plt ? pi : (lt[0] ? ci : i[0]);
+    }
+};
+
+template <int E>
+__global__ void __launch_bounds__(WQ_WARPS * 32)
+ball_wq_kernel(Geom gs, int m, int mpad, float radius, int nsample, int self, int qpw, const float4 *__restrict__ sp,
+               const float4 *__restrict__ tlo, const float4 *__restrict__ thi, const float4 *__restrict__ glo,
+               const float4 *__restrict__ ghi, const float4 *__restrict__ sq, const int *__restrict__ cell_start,
+               const uint32_t *__restrict__ bb, int *__restrict__ idx) {
+    const int lane = threadIdx.x & 31;
+    const int wq0 = (blockIdx.x * WQ_WARPS + (threadIdx.x >> 5)) * qpw;
+    const int n = gs.n;
+    const float r2 = __fmul_rn(radius, radius);
+
+    for (int j = 0; j < qpw; ++j) {
+        const int q = wq0 + j;
+        if (q >= gs.nb * mpad) return;                        // warp-uniform
+        const int b = q / mpad;
+        if (q - b * mpad >= m) continue;
+        const float4 me = __ldg(sq + q);
+        const float qx = me.x, qy = me.y, qz = me.z;
+        WarpIdxList<E> best;
+        best.init(nsample, lane);
+        int ti = 0x7fffffff;                                  // current nsample-th smallest hit index
+        const int tb0 = b * gs.ntb;
+
+        auto process_tile = [&](int t) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int l = (t - tb0) * GT + r * 32 + lane;
+                bool cand = false;
+                int oi = 0x7fffffff;
+                if (l < n) {
+                    const float4 p = __ldg(sp + (long long)t * GT + r * 32 + lane);
+                    // operand order of the reference: new_xyz - xyz (ball_query_gpu.cu:38-40)
+                    const float d = dist2_ref(qx - p.x, qy - p.y, qz - p.z);
+                    oi = __float_as_int(p.w);
+                    cand = d < r2 && oi < ti;
+                }
+                uint32_t mask = __ballot_sync(0xffffffffu, cand);
+                while (mask) {
+                    const int bl = __ffs(mask) - 1;
+                    const int ci = __shfl_sync(0xffffffffu, oi, bl);
+                    best.insert(ci, lane);
+                    ti = best.threshold();
+                    cand = cand && lane != bl && oi < ti;
+                    mask = __ballot_sync(0xffffffffu, cand);
+                }
+            }
+        };
+
+        int t0;
+        if (self) t0 = q / GT;
+        else
+            t0 = (__ldg(cell_start + (((uint32_t)b << (3 * gs.bits)) | cell_of(qx, qy, qz, bb + 8 * b, gs.bits))) +
+                  b * (gs.npad - n)) / GT;
+        t0 = min(max(t0, tb0), tb0 + gs.ntb - 1);
+        process_tile(t0);
+
+        for (int g0 = 0; g0 < gs.ngb; g0 += 32) {
+            const int g = g0 + lane;
+            bool gsel = false;
+            if (g < gs.ngb)
+                gsel = point_box2(qx, qy, qz, __ldg(glo + b * gs.ngb + g), __ldg(ghi + b * gs.ngb + g)) * KG_SAFE < r2;
+            uint32_t gmask = __ballot_sync(0xffffffffu, gsel);
+            while (gmask) {
+                const int gb = __ffs(gmask) - 1;
+                gmask &= gmask - 1;
+                const int lt = (g0 + gb) * TG + lane;
+                const int t = tb0 + lt;
+                bool tsel = false;
+                if (lt < gs.ntb && t != t0) tsel = point_box2(qx, qy, qz, __ldg(tlo + t), __ldg(thi + t)) * KG_SAFE < r2;
+                uint32_t tmask = __ballot_sync(0xffffffffu, tsel);
+                while (tmask) {
+                    const int tbit = __ffs(tmask) - 1;
+                    tmask &= tmask - 1;
+                    process_tile(tb0 + (g0 + gb) * TG + tbit);
+                }
+            }
+        }
+
+        // slots S-nsample .. S-1 hold the hits in ascending index order, INT_MAX where there is none
+        const int shift = 32 * E - nsample;
+        int first = 0x7fffffff;                               // value of slot `shift` (the smallest hit)
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int v = __shfl_sync(0xffffffffu, best.i[e], shift / E);
+            if (e == shift % E) first = v;
+        }
+        if (first == 0x7fffffff) continue;                    // no hit: the row keeps the caller's zeros
+        const long long qorig = (long long)b * m + __float_as_int(me.w);
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int s = lane * E + e - shift;
+            if (s >= 0) idx[qorig * nsample + s] = best.i[e] == 0x7fffffff ? first : best.i[e];
+        }
+    }
+}
+
+// boxes of TG consecutive tile boxes of one cloud
 __global__ void __launch_bounds__(256)
-group_aabb_kernel(int ntiles, int ngroups, const float4 *__restrict__ tlo, const float4 *__restrict__ thi,
+group_aabb_kernel(int ntb, int ngb, int ngroups, const float4 *__restrict__ tlo, const float4 *__restrict__ thi,
                   float4 *__restrict__ glo, float4 *__restrict__ ghi) {
     const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (g >= ngroups) return;
+    const int b = g / ngb, lg = g - b * ngb;
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    const int t = g * TG + lane;
-    if (t < ntiles) {
-        const float4 a = __ldg(tlo + t), b = __ldg(thi + t);
+    const int lt = lg * TG + lane;
+    if (lt < ntb) {
+        const float4 a = __ldg(tlo + b * ntb + lt), c = __ldg(thi + b * ntb + lt);
         lo[0] = a.x; lo[1] = a.y; lo[2] = a.z;
-        hi[0] = b.x; hi[1] = b.y; hi[2] = b.z;
+        hi[0] = c.x; hi[1] = c.y; hi[2] = c.z;
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c)
@@ -472,16 +626,33 @@ group_aabb_kernel(int ntiles, int ngroups, const float4 *__restrict__ tlo, const
     }
 }
 
+// The default memory pool hands freed memory back to the driver at every synchronisation point
+// unless a release threshold is set — a trainer that reads the loss each step (loss.item())
+// would otherwise pay a fresh physical allocation for every scratch buffer of every kNN call
+// (measured: 96 ms per step instead of 22 ms).  Keep the pool's memory: set once per device.
+static void keep_pool_memory() {
+    static bool done[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done[dev] = true;
+}
+
 // per-stream scratch, stream-ordered (cudaMallocAsync pools make this cheap after warm-up)
 struct Scratch {
     cudaStream_t st;
-    void *ptrs[16];
+    void *ptrs[24];
     int count = 0;
     cudaError_t err = cudaSuccess;
-    explicit Scratch(cudaStream_t s) : st(s) {}
+    explicit Scratch(cudaStream_t s) : st(s) { keep_pool_memory(); }
     template <class T>
     T *get(size_t n) {
         void *p = nullptr;
+        if (err == cudaSuccess && count >= 24) err = cudaErrorMemoryAllocation;
         if (err == cudaSuccess) err = cudaMallocAsync(&p, n * sizeof(T) + 16, st);
         if (err == cudaSuccess) ptrs[count++] = p;
         return reinterpret_cast<T *>(p);
@@ -497,74 +668,122 @@ static int pick_bits(int n) {
     return b;
 }
 
-// sort `count` points into Morton-cell order; returns cell_start (exclusive starts) if wanted
-static float4 *sort_points(Scratch &ws, int count, const float *xyz, const uint32_t *bb, int bits,
+// sort nb clouds of `count` points each into Morton-cell order, cloud b at [b*cpad, b*cpad + count);
+// returns cell_start (exclusive starts over all clouds, unpadded) if wanted
+static float4 *sort_points(Scratch &ws, int nb, int count, int cpad, const float *xyz, const uint32_t *bb, int bits,
                            int **cell_start_out) {
-    const int cells = 1 << (3 * bits);
-    uint32_t *cell = ws.get<uint32_t>(count);
+    const long long cells = (long long)nb << (3 * bits);
+    uint32_t *cell = ws.get<uint32_t>((size_t)nb * count);
     int *counts = ws.get<int>(cells);
     int *fill = ws.get<int>(cells);
-    float4 *sorted = ws.get<float4>(count);
+    float4 *sorted = ws.get<float4>((size_t)nb * cpad);
     if (ws.err != cudaSuccess) return nullptr;
     cudaMemsetAsync(counts, 0, sizeof(int) * cells, ws.st);
-    cell_count_kernel<<<div_up(count, 256), 256, 0, ws.st>>>(count, xyz, bb, bits, cell, counts);
-    const int sblocks = div_up(cells, SCAN_CHUNK);
+    dim3 grid(div_up(count, 256), nb);
+    cell_count_kernel<<<grid, 256, 0, ws.st>>>(count, xyz, bb, bits, cell, counts);
+    const int sblocks = (int)div_up_ll(cells, SCAN_CHUNK);
     int *totals = ws.get<int>(sblocks);
     if (ws.err != cudaSuccess) return nullptr;
-    scan_local_kernel<<<sblocks, SCAN_THREADS, 0, ws.st>>>(cells, counts, totals);
+    scan_local_kernel<<<sblocks, SCAN_THREADS, 0, ws.st>>>((int)cells, counts, totals);
     scan_totals_kernel<<<1, SCAN_THREADS, 0, ws.st>>>(sblocks, totals);
-    scan_add_kernel<<<sblocks, SCAN_THREADS, 0, ws.st>>>(cells, counts, totals, fill);
-    scatter_kernel<<<div_up(count, 256), 256, 0, ws.st>>>(count, xyz, cell, fill, sorted);
+    scan_add_kernel<<<sblocks, SCAN_THREADS, 0, ws.st>>>((int)cells, counts, totals, fill);
+    scatter_kernel<<<grid, 256, 0, ws.st>>>(count, cpad - count, xyz, cell, fill, sorted);
     if (cell_start_out) *cell_start_out = counts;
     return sorted;
 }
 
-template <int E>
-static void launch_wq(cudaStream_t st, int n, int m, int nsample, int ntiles, int ngroups, int self, const float4 *sp,
-                      const float4 *tlo, const float4 *thi, const float4 *glo, const float4 *ghi, const float4 *sq,
-                      const int *cell_start, const uint32_t *bb, int bits, int *idx, float *dist2) {
-    // enough warps to fill the machine a few times over; long runs of consecutive queries per warp
-    // only when there are plenty of queries
-    const int qpw = max(1, min(WQ_QPW_MAX, m / (kNumSMs * WQ_WARPS * 8)));
-    const int blocks = div_up(m, WQ_WARPS * qpw);
-    knn_wq_kernel<E><<<blocks, WQ_WARPS * 32, 0, st>>>(n, m, nsample, ntiles, ngroups, self, qpw, sp, tlo, thi, glo, ghi, sq,
-                                                       cell_start, bb, bits, idx, dist2);
+// the structure every search uses: sorted support points + tile / group boxes (+ sorted queries)
+struct Built {
+    Geom gs;
+    uint32_t *bb;
+    float4 *sp, *tlo, *thi, *glo, *ghi;
+    const float4 *sq;
+    int *cell_start;
+    int self, mpad;
+};
+
+// nb clouds: support xyz (nb,n,3), queries new_xyz (nb,m,3).  Returns a cudaError_t.
+static cudaError_t build(Scratch &ws, int nb, int n, int m, const float *xyz, const float *new_xyz, Built &B) {
+    cudaStream_t st = ws.st;
+    Geom &gs = B.gs;
+    gs.nb = nb;
+    gs.n = n;
+    gs.bits = pick_bits(n);
+    gs.ntb = div_up(n, GT);
+    gs.npad = gs.ntb * GT;
+    gs.ngb = div_up(gs.ntb, TG);
+    if (((long long)nb << (3 * gs.bits)) > (1ll << 24)) return cudaErrorInvalidValue;   // scan limit
+    const int ntiles = nb * gs.ntb, ngroups = nb * gs.ngb;
+    B.bb = ws.get<uint32_t>((size_t)nb * 8);
+    B.tlo = ws.get<float4>(ntiles);
+    B.thi = ws.get<float4>(ntiles);
+    B.glo = ws.get<float4>(ngroups);
+    B.ghi = ws.get<float4>(ngroups);
+    if (ws.err != cudaSuccess) return ws.err;
+    bbox_init_kernel<<<div_up(nb * 8, 256), 256, 0, st>>>(nb, B.bb);
+    dim3 bgrid(max(1, min(div_up(n, 1024), div_up(kNumSMs, nb))), nb);
+    bbox_kernel<<<bgrid, 256, 0, st>>>(n, xyz, B.bb);
+    B.cell_start = nullptr;
+    B.sp = sort_points(ws, nb, n, gs.npad, xyz, B.bb, gs.bits, &B.cell_start);
+    if (!B.sp) return ws.err;
+    tile_aabb_kernel<<<div_up(ntiles, 8), 256, 0, st>>>(n, gs.ntb, ntiles, B.sp, B.tlo, B.thi);
+    group_aabb_kernel<<<div_up(ngroups, 8), 256, 0, st>>>(gs.ntb, gs.ngb, ngroups, B.tlo, B.thi, B.glo, B.ghi);
+    B.self = (new_xyz == xyz && m == n) ? 1 : 0;
+    B.sq = B.sp;
+    B.mpad = gs.npad;
+    if (!B.self) {
+        // queries sorted along the same curve so that consecutive warps touch the same tiles (L1 reuse)
+        B.mpad = div_up(m, GT) * GT;
+        B.sq = sort_points(ws, nb, m, B.mpad, new_xyz, B.bb, gs.bits, nullptr);
+        if (!B.sq) return ws.err;
+    }
+    return cudaSuccess;
 }
 
-// single-segment exact kNN with culling; returns 0 or a cudaError_t
+static void search_grid(const Built &B, int m, int &qpw, int &blocks) {
+    // enough warps to fill the machine a few times over; long runs of consecutive queries per warp
+    // only when there are plenty of queries
+    const long long slots = (long long)B.gs.nb * B.mpad;
+    qpw = (int)max(1ll, min((long long)WQ_QPW_MAX, slots / (kNumSMs * WQ_WARPS * 8)));
+    blocks = (int)div_up_ll(slots, WQ_WARPS * qpw);
+}
+
+// exact kNN with culling over nb clouds of n support / m query points; returns 0 or a cudaError_t.
+// idx (nb,m,nsample) holds indices local to the cloud, dist2 the squared distances.
+int knn_grid_batched(int nb, int n, int m, int nsample, const float *xyz, const float *new_xyz, int *idx,
+                     float *dist2, cudaStream_t st) {
+    Scratch ws(st);
+    Built B;
+    cudaError_t e = build(ws, nb, n, m, xyz, new_xyz, B);
+    if (e != cudaSuccess) return (int)e;
+    int qpw, blocks;
+    search_grid(B, m, qpw, blocks);
+#define KNN_WQ_ARGS B.gs, m, B.mpad, nsample, B.self, qpw, B.sp, B.tlo, B.thi, B.glo, B.ghi, B.sq, B.cell_start, B.bb, idx, dist2
+    if (nsample <= 32) knn_wq_kernel<1><<<blocks, WQ_WARPS * 32, 0, st>>>(KNN_WQ_ARGS);
+    else if (nsample <= 64) knn_wq_kernel<2><<<blocks, WQ_WARPS * 32, 0, st>>>(KNN_WQ_ARGS);
+    else knn_wq_kernel<4><<<blocks, WQ_WARPS * 32, 0, st>>>(KNN_WQ_ARGS);
+    return (int)cudaGetLastError();
+}
+
 int knn_grid_single_segment(int n, int m, int nsample, const float *xyz, const float *new_xyz, int *idx,
                             float *dist2, cudaStream_t st) {
+    return knn_grid_batched(1, n, m, nsample, xyz, new_xyz, idx, dist2, st);
+}
+
+// ball query with culling over nb clouds; idx (nb,m,nsample) pre-zeroed by the caller
+int ball_grid_batched(int nb, int n, int m, float radius, int nsample, const float *xyz, const float *new_xyz,
+                      int *idx, cudaStream_t st) {
     Scratch ws(st);
-    const int bits = pick_bits(n);
-    const int ntiles = div_up(n, GT);
-    const int ngroups = div_up(ntiles, TG);
-    uint32_t *bb = ws.get<uint32_t>(8);
-    float4 *tlo = ws.get<float4>(ntiles);
-    float4 *thi = ws.get<float4>(ntiles);
-    float4 *glo = ws.get<float4>(ngroups);
-    float4 *ghi = ws.get<float4>(ngroups);
-    if (ws.err != cudaSuccess) return (int)ws.err;
-    bbox_init_kernel<<<1, 32, 0, st>>>(bb);
-    bbox_kernel<<<min(div_up(n, 1024), kNumSMs), 256, 0, st>>>(n, xyz, bb);
-    int *cell_start = nullptr;
-    float4 *sp = sort_points(ws, n, xyz, bb, bits, &cell_start);
-    if (!sp) return (int)ws.err;
-    tile_aabb_kernel<<<div_up(ntiles, 8), 256, 0, st>>>(n, ntiles, sp, tlo, thi);
-    group_aabb_kernel<<<div_up(ngroups, 8), 256, 0, st>>>(ntiles, ngroups, tlo, thi, glo, ghi);
-    const int self = (new_xyz == xyz && m == n) ? 1 : 0;
-    const float4 *sq = sp;
-    if (!self) {
-        sq = sort_points(ws, m, new_xyz, bb, bits, nullptr);
-        if (!sq) return (int)ws.err;
-    }
-    if (nsample <= 32)
-        launch_wq<1>(st, n, m, nsample, ntiles, ngroups, self, sp, tlo, thi, glo, ghi, sq, cell_start, bb, bits, idx, dist2);
-    else if (nsample <= 64)
-        launch_wq<2>(st, n, m, nsample, ntiles, ngroups, self, sp, tlo, thi, glo, ghi, sq, cell_start, bb, bits, idx, dist2);
-    else
-        launch_wq<4>(st, n, m, nsample, ntiles, ngroups, self, sp, tlo, thi, glo, ghi, sq, cell_start, bb, bits, idx, dist2);
-    cudaError_t e = cudaGetLastError();
-    return (int)e;
+    Built B;
+    cudaError_t e = build(ws, nb, n, m, xyz, new_xyz, B);
+    if (e != cudaSuccess) return (int)e;
+    int qpw, blocks;
+    search_grid(B, m, qpw, blocks);
+#define BALL_WQ_ARGS B.gs, m, B.mpad, radius, nsample, B.self, qpw, B.sp, B.tlo, B.thi, B.glo, B.ghi, B.sq, B.cell_start, B.bb, idx
+    if (nsample <= 32) ball_wq_kernel<1><<<blocks, WQ_WARPS * 32, 0, st>>>(BALL_WQ_ARGS);
+    else if (nsample <= 64) ball_wq_kernel<2><<<blocks, WQ_WARPS * 32, 0, st>>>(BALL_WQ_ARGS);
+    else ball_wq_kernel<4><<<blocks, WQ_WARPS * 32, 0, st>>>(BALL_WQ_ARGS);
+    return (int)cudaGetLastError();
 }
 
 }  // namespace amc3d

@@ -243,8 +243,12 @@ def run_ours(args):
     stats_layout = amdist.PackedStats(13)
     buckets = amdist.GradBuckets(int(args.grad_mb * 1e6 / 4), dev) if world > 1 and args.grad_mb > 0 else None
 
-    def one_step(e2e=False):
-        if e2e:
+    use_graph = not args.no_graph
+
+    def one_step(e2e=False, graph=False):
+        if graph:
+            loss = replay.step_graph(replay.h_xyz, replay.h_labels) if e2e else replay.step_graph()
+        elif e2e:
             xyz = replay.h_xyz.to(dev, non_blocking=True)
             labels = replay.h_labels.to(dev, non_blocking=True)
             loss = replay.step(xyz, labels)
@@ -260,7 +264,7 @@ def run_ours(args):
                 buckets.wait()
         return loss
 
-    def timed(n_steps, e2e):
+    def timed(n_steps, e2e, graph):
         if world > 1:
             tdist.barrier()
         torch.cuda.synchronize()
@@ -268,7 +272,7 @@ def run_ours(args):
         e0.record()
         last = None
         for _ in range(n_steps):
-            loss = one_step(e2e)
+            loss = one_step(e2e, graph)
             if e2e:
                 last = float(loss.item())        # device -> host read of the step's result
         e1.record()
@@ -281,19 +285,34 @@ def run_ours(args):
             tdist.barrier()
         return ms, last
 
-    for _ in range(max(args.warmup, 3)):
-        one_step(False)
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        one_step(False, False)
     torch.cuda.synchronize()
+
+    # eager arm (every operator call issued from Python each step) — reported beside the graph arm
+    e2e_steps = max(1, min(args.steps, 10))
+    eager_ms, _ = timed(e2e_steps, False, False)
+    one_step(True, False)
+    eager_e2e_ms, last_loss = timed(e2e_steps, True, False)
+    eager = {"ms_per_step": eager_ms / e2e_steps, "e2e_ms_per_step": eager_e2e_ms / e2e_steps, "steps": e2e_steps}
+
+    l0 = _capi.LAUNCHES
+    one_step(False, False)
+    launches = _capi.LAUNCHES - l0
+    if use_graph:
+        replay.capture(warmup=1)
+        launches = replay.graph_launches
+        for _ in range(warm):
+            one_step(False, True)
+        torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = _capi.LAUNCHES
-    ms_total, _ = timed(args.steps, False)
-    launches = (_capi.LAUNCHES - l0) // max(args.steps, 1)
-    e2e_steps = max(1, min(args.steps, 10))
-    one_step(True)
-    ms_e2e, last_loss = timed(e2e_steps, True)
+    ms_total, _ = timed(args.steps, False, use_graph)
+    one_step(True, use_graph)
+    ms_e2e, last_loss = timed(e2e_steps, True, use_graph)
     clocks = sampler.stop() if rank == 0 else None
 
     ms_step = ms_total / args.steps
@@ -360,7 +379,8 @@ def run_ours(args):
                        "grad_allreduce_mb": args.grad_mb if world > 1 else 0, "loss": last_loss},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": replay.h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / e2e_steps},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm,
+            "gpu_launches": int(launches), "mode": "cuda-graph replay of the whole step" if use_graph else "eager",
+            "eager": eager, "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm,
             "kernels": kernels, "kernel_ms_per_step": round(total_ms, 3), "cpu_baseline": cpu_baseline}
     print(json.dumps(line))
     if world > 1:
@@ -378,6 +398,7 @@ def main():
     ap.add_argument("--k", type=int, default=16)
     ap.add_argument("--grad-mb", type=float, default=166.3, help="flat gradient all-reduce per step (N>1): PointNeXt-XL FP32 grads")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager (per-call Python) step instead of the CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -162,7 +162,9 @@ def test_fps_exact_tie_order(n, m):
 
 # ------------------------------------------------------------------ ball query
 @pytest.mark.parametrize("n,m,r,ns", [(6000, 1500, 0.1, 32), (6000, 6000, 0.2, 32), (1500, 375, 0.4, 32),
-                                      (375, 93, 0.8, 16), (3000, 700, 0.02, 8), (2000, 2000, 5.0, 32)])
+                                      (375, 93, 0.8, 16), (3000, 700, 0.02, 8), (2000, 2000, 5.0, 32),
+                                      (24000, 6000, 0.1, 32), (4096, 4096, 0.3, 64), (3000, 3000, 0.25, 100),
+                                      (2500, 100, 10.0, 32)])
 def test_ball_query(n, m, r, ns):
     from amcontrast3d_b200.layers import ball_query
     xyz, _ = scenes.batch_of_scenes(3, n, "surface", first_scene=4)
@@ -173,8 +175,22 @@ def test_ball_query(n, m, r, ns):
     assert np.array_equal(idx.cpu().numpy(), ref)
 
 
+def test_ball_query_same_tensor_and_lattice():
+    """query set == support set (LocalAggregation): the culled path reuses the sorted support points as
+    queries; lattice coordinates put many points at exactly d2 == r^2 (strict '<' must exclude them)."""
+    from amcontrast3d_b200.layers import ball_query
+    xyz, _ = scenes.batch_of_scenes(2, 6000, "surface", first_scene=9)
+    t = _t(xyz)
+    assert np.array_equal(ball_query(0.2, 32, t, t).cpu().numpy(), oo.ball_query(0.2, 32, xyz, xyz))
+    lat = np.random.default_rng(1).integers(0, 24, size=(2, 5000, 3)).astype(np.float32) * 0.125
+    tl = _t(lat)
+    for r in (0.125, 0.25, 0.375):
+        assert np.array_equal(ball_query(r, 16, tl, tl).cpu().numpy(), oo.ball_query(r, 16, lat, lat))
+
+
 # ------------------------------------------------------------------ three_nn / interpolate
-@pytest.mark.parametrize("n,m", [(375, 93), (1500, 375), (6000, 1500), (700, 2), (50, 1)])
+@pytest.mark.parametrize("n,m", [(375, 93), (1500, 375), (6000, 1500), (700, 2), (50, 1), (12000, 3000), (5000, 5000),
+                                 (100, 2500)])
 def test_three_nn(n, m):
     from amcontrast3d_b200.layers import three_nn
     xyz, _ = scenes.batch_of_scenes(2, max(n, m), "surface", first_scene=6)
