@@ -53,6 +53,8 @@ SIGNATURES = {
     "amc3d_three_nn": [_I, _I, _I, _P, _P, _P, _P, _P],
     "amc3d_three_interpolate": [_I, _I, _I, _I, _P, _P, _P, _P, _P],
     "amc3d_three_interpolate_grad": [_I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "amc3d_three_interpolate_ws": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
+    "amc3d_three_interpolate_grad_ws": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "amc3d_knnquery": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "amc3d_grouping_forward": [_I, _I, _I, _P, _P, _P, _P],
     "amc3d_grouping_backward": [_I, _I, _I, _P, _P, _P, _P],
@@ -118,6 +120,10 @@ def _kernels_in(name: str, args) -> int:
     if name == "amc3d_group_points_ws":
         return 2 if args[-2] else 1            # transpose + gather with a workspace
     if name == "amc3d_group_points_grad_ws":
+        return 2 if args[-2] else 1            # scatter + transpose-accumulate (plus a memset)
+    if name == "amc3d_three_interpolate_ws":
+        return 2 if args[-2] else 1            # transpose + interpolate
+    if name == "amc3d_three_interpolate_grad_ws":
         return 2 if args[-2] else 1            # scatter + transpose-accumulate (plus a memset)
     if name == "amc3d_refine_backward":
         return 2

@@ -89,6 +89,50 @@ ball_query_kernel(int n, int m, float radius, int nsample, const float *__restri
         for (int l = cnt; l < nsample; ++l) row[l] = first;
 }
 
+// Same semantics, one WARP per query: the 32 lanes test 32 consecutive support points at a time, a
+// ballot gives the hits in index order, and the scan stops as soon as nsample hits are in — for the
+// small clouds of the deep levels (n <= 2048) this exposes 32x more parallelism than a thread per
+// query and makes the early exit effective (a thread-per-query CTA runs until its slowest query).
+__global__ void __launch_bounds__(256)
+ball_query_warp_kernel(int n, int m, float radius, int nsample, const float *__restrict__ new_xyz,
+                       const float *__restrict__ xyz, int *__restrict__ idx) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.y;
+    const int q = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (q >= m) return;
+    xyz += 3ll * b * n;
+    const float *qp = new_xyz + 3ll * ((long long)b * m + q);
+    int *row = idx + ((long long)b * m + q) * nsample;
+    const float r2 = __fmul_rn(radius, radius);
+    const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
+    const uint32_t lt = (1u << lane) - 1u;
+    int cnt = 0, first = -1;
+    for (int k0 = 0; k0 < n && cnt < nsample; k0 += 64) {
+        bool hit[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = k0 + h * 32 + lane;
+            hit[h] = false;
+            if (k < n) {
+                const float *p = xyz + 3ll * k;
+                hit[h] = dist2_ref(qx - __ldg(p), qy - __ldg(p + 1), qz - __ldg(p + 2)) < r2;
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t mask = __ballot_sync(0xffffffffu, hit[h]);
+            if (mask) {
+                if (first < 0) first = k0 + h * 32 + __ffs(mask) - 1;
+                const int pos = cnt + __popc(mask & lt);
+                if (hit[h] && pos < nsample) row[pos] = k0 + h * 32 + lane;
+                cnt += __popc(mask);
+            }
+        }
+    }
+    if (first >= 0)
+        for (int l = min(cnt, nsample) + lane; l < nsample; l += 32) row[l] = first;
+}
+
 // Semantics (interpolate_gpu.cu:37-58): ascending k, strict '<' cascade over three bests
 // initialised to 1e40 (double) / index 0.  Floats compared as doubles compare identically,
 // and (float)1e40 = +inf, so float bests initialised to +inf reproduce it exactly.
@@ -183,8 +227,14 @@ extern "C" int amc3d_ball_query(int b, int n, int m, float radius, int nsample,
         }
         return check_launch("ball_query");
     }
-    dim3 grid(div_up(m, BQ_THREADS), b);
-    ball_query_kernel<<<grid, BQ_THREADS, 0, as_stream(stream)>>>(n, m, radius, nsample, new_xyz, xyz, idx);
+    static const bool thread_per_query = getenv("AMC3D_BALL_THREAD") != nullptr;   // for measurements
+    if (thread_per_query) {
+        dim3 grid(div_up(m, BQ_THREADS), b);
+        ball_query_kernel<<<grid, BQ_THREADS, 0, as_stream(stream)>>>(n, m, radius, nsample, new_xyz, xyz, idx);
+    } else {
+        dim3 grid(div_up(m, 8), b);
+        ball_query_warp_kernel<<<grid, 256, 0, as_stream(stream)>>>(n, m, radius, nsample, new_xyz, xyz, idx);
+    }
     return check_launch("ball_query");
 }
 

@@ -84,6 +84,19 @@ __device__ __forceinline__ uint32_t lds_b32(uint32_t a) {
 __device__ __forceinline__ void sts_v4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
+__device__ __forceinline__ uint2 lds_v2(uint32_t a) {
+    uint2 r;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a) : "memory");
+    return r;
+}
+__device__ __forceinline__ void sts_v2(uint32_t a, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void st_async_v2(uint32_t raddr, uint32_t rbar, uint32_t a, uint32_t b) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1,%2}, [%3];"
+                 ::"r"(raddr), "r"(a), "r"(b), "r"(rbar)
+                 : "memory");
+}
 __device__ __forceinline__ void sts_b32(uint32_t a, uint32_t x) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(x) : "memory");
 }
@@ -106,7 +119,7 @@ __device__ __forceinline__ uint32_t tie_key(int k, int log2bs) {
 // A candidate is 20 bytes in a 32-byte slot: {value bits, index, x, y} {z}.  The value is a
 // non-negative float, so its bit pattern orders like the value.
 constexpr int CAND_BYTES = 32;
-constexpr int CAND_TX = 20;      // bytes actually transferred per candidate
+constexpr int CAND_TX = 24;      // bytes actually transferred per candidate: {v,k,x,y} {z,bound}
 
 // argmax over the candidates held one per lane (lanes >= count hold v = 0, k = -1): returns the
 // lane of the winner.  The tie key is only evaluated when two candidates share the maximum.
@@ -117,6 +130,26 @@ __device__ __forceinline__ int cand_argmax(uint32_t v, int k, int log2bs) {
     const uint32_t tb = v == gv ? tie_key(k, log2bs) : 0xffffffffu;
     const uint32_t gt = __reduce_min_sync(0xffffffffu, tb);
     return __ffs(__ballot_sync(0xffffffffu, v == gv && tb == gt)) - 1;
+}
+
+// largest and second-largest of N non-negative values (second = 0 when N == 1), as a merge tree
+template <int N>
+__device__ __forceinline__ void top2(const float (&t)[N], float &v1, float &v2) {
+    float a[N], b[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { a[i] = t[i]; b[i] = 0.f; }
+#pragma unroll
+    for (int w = N; w > 1; w = (w + 1) / 2) {
+#pragma unroll
+        for (int i = 0; i < w / 2; ++i) {
+            const int o = w - 1 - i;
+            const float hi = fmaxf(a[i], a[o]), lo = fminf(a[i], a[o]);
+            b[i] = fmaxf(lo, fmaxf(b[i], b[o]));
+            a[i] = hi;
+        }
+    }
+    v1 = a[0];
+    v2 = b[0];
 }
 
 template <int N>
@@ -141,12 +174,16 @@ __device__ __forceinline__ float tree_max(const float (&t)[N]) {
 template <int CS, int PPT, int NW>
 __global__ void __launch_bounds__(NW * 32)
 fps_cluster_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, float *__restrict__ temp,
-                   int *__restrict__ idxs) {
+                   int *__restrict__ idxs, int dbg) {
     constexpr int NT = NW * 32;
+    constexpr int NC = CS * NW;              // candidates per round: one per warp of the cluster
+    constexpr int CPL = (NC + 31) / 32;      // candidates per lane
+    static_assert(NC <= 256, "too many candidates");
     extern __shared__ float4 s_pts[];                              // [PPT][NT] copy of this CTA's points
     __shared__ __align__(16) unsigned char s_warp[2][NW][CAND_BYTES];   // per-warp candidates
-    __shared__ __align__(16) unsigned char s_exch[2][CS][CAND_BYTES];   // per-CTA candidates of the cluster
+    __shared__ __align__(16) unsigned char s_exch[2][NC][CAND_BYTES];   // every warp's candidate, whole cluster
     __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ __align__(16) unsigned char s_picks[NW][(NC < 64 ? NC : 64) * 16];   // this round's picks, one copy per warp
 
     const int tid = (int)pin(threadIdx.x), lane = tid & 31, warp = tid >> 5;
     const int rank = (int)cluster_ctarank();
@@ -155,16 +192,20 @@ fps_cluster_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, floa
     temp += (long long)batch * n;
     idxs += (long long)batch * m;
 
-    const int chunk = div_up(n, CS);
-    const int base = rank * chunk;
+    // Point k of the scene belongs to CTA k % CS, warp (k / CS) % NW, lane (k / (CS*NW)) % 32, slot
+    // k / (CS*NW*32): consecutive indices land in different warps.  PointNeXt runs FPS on clouds that
+    // are already in FPS order (every level below the first), where the next picks ARE the next
+    // indices — with a blocked layout they would all sit in one warp, its runner-up bound would
+    // equal the next pick and every round would yield a single pick.
+    const int kbase = rank + CS * (warp + NW * lane);     // index of slot 0
+    constexpr int KSTRIDE = CS * NW * 32;                 // index distance between slots
 
     float x[PPT], y[PPT], z[PPT], t[PPT];
     bool any_valid = false;
 #pragma unroll
     for (int s = 0; s < PPT; ++s) {
-        const int l = s * NT + tid;
-        const int k = base + l;
-        if (l < chunk && k < n) {
+        const int k = kbase + s * KSTRIDE;
+        if (k < n) {
             x[s] = __ldg(xyz + 3ll * k);
             y[s] = __ldg(xyz + 3ll * k + 1);
             z[s] = __ldg(xyz + 3ll * k + 2);
@@ -188,7 +229,9 @@ fps_cluster_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, floa
     // a warp without a single valid point publishes a losing candidate once and only keeps the barriers
     if (lane == 0) {
         sts_v4(smem_u32(&s_warp[0][warp][0]), 0u, 0xffffffffu, 0u, 0u);
+        sts_v4(smem_u32(&s_warp[0][warp][16]), 0u, 0u, 0u, 0u);
         sts_v4(smem_u32(&s_warp[1][warp][0]), 0u, 0xffffffffu, 0u, 0u);
+        sts_v4(smem_u32(&s_warp[1][warp][16]), 0u, 0u, 0u, 0u);
     }
     __syncthreads();
     cluster_sync_all();
@@ -202,23 +245,31 @@ fps_cluster_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, floa
     const uint32_t a_warp0 = pin(smem_u32(&s_warp[0][0][0]));      // + par*NW*32 + w*32
     const uint32_t a_exch0 = pin(smem_u32(&s_exch[0][0][0]));      // + par*CS*32 + r*32
     const uint32_t lbar0 = pin(smem_u32(&s_bar[0])), lbar1 = pin(smem_u32(&s_bar[1]));
+    const uint32_t a_picks = pin(smem_u32(&s_picks[warp][0]));
+    const int mm = (int)pin((uint32_t)m);
     // warp 0, lane r delivers this CTA's candidate to CTA r of the cluster
     const uint32_t peer = lane < CS ? lane : 0;
-    const uint32_t dst0 = mapa_u32(a_exch0 + rank * CAND_BYTES, peer);
-    const uint32_t dst1 = mapa_u32(a_exch0 + (CS + rank) * CAND_BYTES, peer);
+    const uint32_t dst0 = mapa_u32(a_exch0 + rank * NW * CAND_BYTES, peer);
+    const uint32_t dst1 = mapa_u32(a_exch0 + (NC + rank * NW) * CAND_BYTES, peer);
     const uint32_t rbar0 = mapa_u32(lbar0, peer), rbar1 = mapa_u32(lbar1, peer);
 
-    uint32_t par = 0, phase = 0;
-    for (int j = 1; j < m; ++j) {
-        // ---- running distance update ------------------------------------------------------------
+    // the first pick (index 0) is applied before the loop, so that t[] is always up to date
+    // with every pick made so far when a round starts
+    if (m > 1) {
 #pragma unroll
-        for (int s = 0; s < PPT; ++s) {
-            const float d = dist2_ref(x[s] - x1, y[s] - y1, z[s] - z1);
-            t[s] = fminf(d, t[s]);
-        }
+        for (int s = 0; s < PPT; ++s) t[s] = fminf(dist2_ref(x[s] - x1, y[s] - y1, z[s] - z1), t[s]);
+    }
+
+    uint32_t par = 0, phase = 0;
+    int j = 1, rounds = 0;
+    while (j < m) {
+        ++rounds;
+        // ---- A. this thread's best and second-best, the warp's candidate and its runner-up bound ----
         const uint32_t my_warp_slot = a_warp0 + ((CS == 1 ? par * NW : 0) + warp) * CAND_BYTES;
         if (warp_valid) {
-            const uint32_t vb = __float_as_uint(tree_max(t));
+            float v1, v2;
+            top2(t, v1, v2);
+            const uint32_t vb = __float_as_uint(v1);
             const uint32_t wv = __reduce_max_sync(0xffffffffu, vb);
             const bool mine = vb == wv;
             uint32_t smask = 0;                                   // slots of this thread equal to the warp maximum
@@ -234,9 +285,8 @@ fps_cluster_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, floa
                 if (mine) {
 #pragma unroll
                     for (int s = 0; s < PPT; ++s) {
-                        const int l = s * NT + tid;
-                        const bool valid = l < chunk && base + l < n;      // padding slots never win a tie
-                        const uint32_t tbs = valid ? tie_key(base + l, log2bs) : 0xffffffffu;
+                        const int k = kbase + s * KSTRIDE;                 // padding slots never win a tie
+                        const uint32_t tbs = k < n ? tie_key(k, log2bs) : 0xffffffffu;
                         if (((smask >> s) & 1u) && tbs < mytb) { mytb = tbs; bslot = s; }
                     }
                 }
@@ -244,66 +294,120 @@ fps_cluster_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, floa
                 src = __ffs(__ballot_sync(0xffffffffu, mine && mytb == wtb)) - 1;
                 if (wtb == 0xffffffffu && lane == src) bslot = -1;          // only padding slots: losing candidate
             }
-            // ---- the candidate lane publishes (value, index, xyz) for its warp ----------------
+            // upper bound of every point of this warp other than the candidate
+            const uint32_t sec = __reduce_max_sync(0xffffffffu, __float_as_uint(lane == src ? v2 : v1));
             if (lane == src) {
                 if (bslot >= 0) {
                     const uint4 cp = lds_v4(a_pts + bslot * (NT * 16));
-                    sts_v4(my_warp_slot, wv, (uint32_t)(base + bslot * NT + tid), cp.x, cp.y);
-                    sts_b32(my_warp_slot + 16, cp.z);
+                    sts_v4(my_warp_slot, wv, (uint32_t)(kbase + bslot * KSTRIDE), cp.x, cp.y);
+                    sts_v2(my_warp_slot + 16, cp.z, sec);
                 } else {
                     sts_v4(my_warp_slot, 0u, 0xffffffffu, 0u, 0u);
+                    sts_v2(my_warp_slot + 16, 0u, sec);
                 }
             }
         }
-        uint32_t cv = 0;
-        int ck = -1;
-        uint32_t a_cands;      // base of the candidate array every warp reduces below
+        // ---- candidates of the whole scene, CPL per lane: (value, index, xyz) and the bound U ----
+        uint32_t cv[CPL], cu = 0;
+        int ck[CPL];
+        float cx[CPL], cy[CPL], cz[CPL];
+        uint32_t a_c;
         if (CS == 1) {
-            // single CTA: one barrier, then every warp reduces the NW warp candidates itself
+            // single CTA: one barrier, then every warp works on the NW warp candidates itself
             __syncthreads();
-            a_cands = a_warp0 + par * NW * CAND_BYTES;
-            if (lane < NW) {
-                cv = lds_b32(a_cands + lane * CAND_BYTES);
-                ck = (int)lds_b32(a_cands + lane * CAND_BYTES + 4);
-            }
+            a_c = a_warp0 + par * NW * CAND_BYTES;
         } else {
-            // warps 1.. only signal; warp 0 collects, picks the CTA's candidate and pushes it into
-            // every CTA of the cluster (st.async completes a transaction on the receiver's mbarrier)
+            // every warp pushes its own candidate straight into every CTA of the cluster (st.async
+            // completes a transaction on the receiver's mbarrier): lane r < CS delivers to CTA r
             const uint32_t lbar = par ? lbar1 : lbar0;
-            if (warp != 0) {
-                asm volatile("bar.arrive 1, %0;" ::"r"(NT) : "memory");
-            } else {
-                asm volatile("bar.sync 1, %0;" ::"r"(NT) : "memory");
-                if (lane == 0) mbar_expect_tx(lbar, CS * CAND_TX);
-                uint32_t wvv = 0;
-                int wk = -1;
-                if (lane < NW) {
-                    wvv = lds_b32(a_warp0 + lane * CAND_BYTES);
-                    wk = (int)lds_b32(a_warp0 + lane * CAND_BYTES + 4);
-                }
-                const int wl = cand_argmax(wvv, wk, log2bs);
-                if (lane < CS) {
-                    const uint4 w = lds_v4(a_warp0 + wl * CAND_BYTES);
-                    const uint32_t wz = lds_b32(a_warp0 + wl * CAND_BYTES + 16);
-                    const uint32_t dst = par ? dst1 : dst0, rbar = par ? rbar1 : rbar0;
-                    st_async_v4(dst, rbar, w.x, w.y, w.z, w.w);
-                    st_async_b32(dst + 16, rbar, wz);
-                }
+            if (tid == 0) mbar_expect_tx(lbar, NC * CAND_TX);
+            __syncwarp();
+            if (lane < CS) {
+                const uint4 w = lds_v4(my_warp_slot);
+                const uint2 w2 = lds_v2(my_warp_slot + 16);
+                const uint32_t dst = (par ? dst1 : dst0) + warp * CAND_BYTES, rbar = par ? rbar1 : rbar0;
+                st_async_v4(dst, rbar, w.x, w.y, w.z, w.w);
+                st_async_v2(dst + 16, rbar, w2.x, w2.y);
             }
             mbar_wait(lbar, phase);
-            a_cands = a_exch0 + par * CS * CAND_BYTES;
-            if (lane < CS) {
-                cv = lds_b32(a_cands + lane * CAND_BYTES);
-                ck = (int)lds_b32(a_cands + lane * CAND_BYTES + 4);
+            a_c = a_exch0 + par * NC * CAND_BYTES;
+        }
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            cv[c] = 0; ck[c] = -1; cx[c] = cy[c] = cz[c] = 0.f;
+            if (c * 32 + lane < NC) {
+                const uint4 q = lds_v4(a_c + (c * 32 + lane) * CAND_BYTES);
+                const uint2 d = lds_v2(a_c + (c * 32 + lane) * CAND_BYTES + 16);
+                cv[c] = q.x; ck[c] = (int)q.y; cx[c] = __uint_as_float(q.z); cy[c] = __uint_as_float(q.w);
+                cz[c] = __uint_as_float(d.x);
+                cu = max(cu, d.y);
             }
         }
-        // ---- every warp finds the winner among the candidates and reads its coordinates ---------
-        const int gl = cand_argmax(cv, ck, log2bs);
-        const uint4 win = lds_v4(a_cands + gl * CAND_BYTES);
-        z1 = __uint_as_float(lds_b32(a_cands + gl * CAND_BYTES + 16));
-        x1 = __uint_as_float(win.z);
-        y1 = __uint_as_float(win.w);
-        if (rank == 0 && tid == 0) idxs[j] = (int)win.y;
+        const uint32_t U = __reduce_max_sync(0xffffffffu, cu);   // no point outside the candidates exceeds U
+
+        // ---- B. exact FPS on the candidate set for as long as its maximum provably beats every other
+        //         point: the first pick is the global arg-max; a further pick is valid while its value
+        //         is > U, because values only shrink.  This loop is one dependent chain per pick
+        //         (arg-max -> winner's xyz -> candidates' new values), so it touches the candidates only;
+        //         the picks are parked in shared memory and applied to this thread's points afterwards,
+        //         where PPT independent chains keep the FP32 pipe busy.
+        const int j0 = j;
+        int q = 0, qa = 0;                 // picks made / picks to apply in this round
+        while (true) {
+            // this lane's best entry (first one on equal values), then the warp's
+            uint32_t bv = cv[0];
+            int be = 0;
+#pragma unroll
+            for (int c = 1; c < CPL; ++c)
+                if (cv[c] > bv) { bv = cv[c]; be = c; }
+            const uint32_t val = __reduce_max_sync(0xffffffffu, bv);
+            if (q > 0 && !(val > U)) break;
+            int neq = 0;                   // entries of this lane equal to the maximum
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) neq += cv[c] == val ? 1 : 0;
+            const uint32_t gb = __ballot_sync(0xffffffffu, neq > 0);
+            const uint32_t g2 = __ballot_sync(0xffffffffu, neq > 1);
+            int gl = __ffs(gb) - 1;
+            if (((gb & (gb - 1)) | g2) != 0) {
+                // equal maxima (rare): the reference's tie order decides
+                uint32_t tb = 0xffffffffu;
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) {
+                    const uint32_t kc = cv[c] == val ? tie_key(ck[c], log2bs) : 0xffffffffu;
+                    if (kc < tb) { tb = kc; be = c; }
+                }
+                const uint32_t gt = __reduce_min_sync(0xffffffffu, tb);
+                gl = __ffs(__ballot_sync(0xffffffffu, tb == gt)) - 1;
+            }
+            float sx = cx[0], sy = cy[0], sz = cz[0];
+            int sk = ck[0];
+#pragma unroll
+            for (int c = 1; c < CPL; ++c)
+                if (be == c) { sx = cx[c]; sy = cy[c]; sz = cz[c]; sk = ck[c]; }
+            x1 = __shfl_sync(0xffffffffu, sx, gl);
+            y1 = __shfl_sync(0xffffffffu, sy, gl);
+            z1 = __shfl_sync(0xffffffffu, sz, gl);
+            if (lane == gl)
+                sts_v4(a_picks + q * 16, __float_as_uint(sx), __float_as_uint(sy), __float_as_uint(sz), (uint32_t)sk);
+            ++q;
+            ++j;
+            if (j >= mm) break;            // like the reference, the last pick is never applied to temp
+            qa = q;
+            if (q == (NC < 64 ? NC : 64)) break;   // pick buffer full: go on in the next round
+#pragma unroll
+            for (int c = 0; c < CPL; ++c)
+                cv[c] = min(cv[c], __float_as_uint(dist2_ref(cx[c] - x1, cy[c] - y1, cz[c] - z1)));
+        }
+        __syncwarp();
+        if (rank == 0 && warp == 0 && lane < q) idxs[j0 + lane] = (int)lds_b32(a_picks + lane * 16 + 12);
+        if (NC > 32 && rank == 0 && warp == 0 && lane + 32 < q) idxs[j0 + 32 + lane] = (int)lds_b32(a_picks + (lane + 32) * 16 + 12);
+#pragma unroll 2
+        for (int qq = 0; qq < qa; ++qq) {
+            const uint4 pk = lds_v4(a_picks + qq * 16);
+            const float px = __uint_as_float(pk.x), py = __uint_as_float(pk.y), pz = __uint_as_float(pk.z);
+#pragma unroll
+            for (int s = 0; s < PPT; ++s) t[s] = fminf(dist2_ref(x[s] - px, y[s] - py, z[s] - pz), t[s]);
+        }
         par ^= 1;
         if (par == 0) phase ^= 1;
     }
@@ -311,10 +415,10 @@ fps_cluster_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, floa
     // the reference leaves the final running distances in temp
 #pragma unroll
     for (int s = 0; s < PPT; ++s) {
-        const int l = s * NT + tid;
-        const int k = base + l;
-        if (l < chunk && k < n) temp[k] = t[s];
+        const int k = kbase + s * KSTRIDE;
+        if (k < n) temp[k] = t[s];
     }
+    if (dbg && rank == 0 && tid == 0) temp[0] = (float)rounds;   // AMC3D_FPS_DEBUG: exchange rounds instead of temp[0]
     cluster_sync_all();  // no CTA may exit while a peer can still address its shared memory
 }
 
@@ -387,7 +491,8 @@ static cudaError_t launch_cluster(int b, int n, int m, int log2bs, const float *
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, n, m, log2bs, xyz, temp, idx);
+    static const int dbg = getenv("AMC3D_FPS_DEBUG") != nullptr;
+    return cudaLaunchKernelEx(&cfg, kern, n, m, log2bs, xyz, temp, idx, dbg);
 }
 
 #define FPS_ARGS b, n, m, log2bs, xyz, temp, idx, st
@@ -412,7 +517,7 @@ static cudaError_t launch_for_ppt(int ppt, int b, int n, int m, int log2bs, cons
 template <int CS>
 static cudaError_t launch_for_nw(int nw, int b, int n, int m, int log2bs, const float *xyz, float *temp, int *idx,
                                  cudaStream_t st) {
-    const int ppt = div_up(div_up(n, CS), nw * 32);
+    const int ppt = div_up(n, CS * nw * 32);
     if (nw == 4) return launch_for_ppt<CS, 4>(ppt, FPS_ARGS);
     if (nw == 8) return launch_for_ppt<CS, 8>(ppt, FPS_ARGS);
     return launch_for_ppt<CS, 16>(ppt, FPS_ARGS);
@@ -448,9 +553,14 @@ extern "C" int amc3d_furthest_point_sampling(int b, int n, int m, const float *x
     // cluster size and warps per CTA: as much parallelism as pays off (each round costs one
     // exchange regardless); AMC3D_FPS_CS / AMC3D_FPS_NW override the choice for experiments
     static const int env_cs = env_int("AMC3D_FPS_CS", 0), env_nw = env_int("AMC3D_FPS_NW", 0);
-    int cs = n > 1536 ? 16 : (n > 384 ? 4 : 1);
+    // (measured, tools/prof_fps.py: 4 warps beat 8 at equal n — the exchange cost grows with the number
+    // of sending warps — so more warps only when the points no longer fit 4 warps' registers)
+    int cs = n > 1536 ? 16 : (n > 768 ? 8 : (n > 192 ? 4 : 1));
     int nw = 4;
-    while (nw < 16 && div_up(div_up(n, cs), nw * 32) > 16) nw *= 2;
+    if (div_up(n, cs * nw * 32) > 32) {
+        nw = 8;
+        if (div_up(n, cs * nw * 32) > 24) nw = 16;
+    }
     if (env_cs == 1 || env_cs == 4 || env_cs == 8 || env_cs == 16) cs = env_cs;
     if (env_nw == 4 || env_nw == 8 || env_nw == 16) nw = env_nw;
     cudaError_t e = launch_for_cs(cs, nw, FPS_ARGS);

@@ -322,6 +322,133 @@ group_bwd_tma_kernel(int C, int N, int P, const float *__restrict__ grad_out, co
 }
 
 // ---------------------------------------------------------------------------------------
+// three_interpolate through the same machinery: the (B,C,m) source is transposed to (B,m,C), a
+// warp reads the three neighbour rows of a position as three coalesced 128-byte loads (lane =
+// channel), the weighted sum uses the reference's FMA chain, the 32 x 256 output tile leaves by
+// bulk-async stores.  idx / weight of the tile's 256 positions are staged in shared memory once.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+interp_fwd_tma_kernel(int C, int M, int N, const float *__restrict__ srcT, const int *__restrict__ idx,
+                      const float *__restrict__ weight, float *__restrict__ out) {
+    extern __shared__ __align__(128) float tile[];   // [TC][FWD_LD] then idx[256*3], w[256*3]
+    int *s_idx = reinterpret_cast<int *>(tile + TC * FWD_LD);
+    float *s_w = reinterpret_cast<float *>(s_idx + TP * 3);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * TC;
+    const int p0 = blockIdx.x * TP;
+    const int npos = min(TP, N - p0);                 // multiple of 4 (host checks N % 4 == 0)
+    const long long o3 = 3ll * ((long long)b * N + p0);
+    for (int i = threadIdx.x; i < npos * 3; i += 256) {
+        s_idx[i] = __ldg(idx + o3 + i);
+        s_w[i] = __ldg(weight + o3 + i);
+    }
+    __syncthreads();
+    const int cc = min(c0 + lane, C - 1);
+    const float *src = srcT + (long long)b * M * C + cc;
+    const int wpos = min(32, npos - warp * 32);
+    float *trow = tile + lane * FWD_LD + warp * 32;
+    for (int o = 0; o * 4 < wpos; ++o) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int p = warp * 32 + o * 4 + u;
+            const int i0 = s_idx[3 * p], i1 = s_idx[3 * p + 1], i2 = s_idx[3 * p + 2];
+            const float w0 = s_w[3 * p], w1 = s_w[3 * p + 1], w2 = s_w[3 * p + 2];
+            const float f0 = __ldg(src + (long long)i0 * C), f1 = __ldg(src + (long long)i1 * C),
+                        f2 = __ldg(src + (long long)i2 * C);
+            v[u] = __fmaf_rn(w2, f2, __fmaf_rn(w0, f0, __fmul_rn(w1, f1)));   // interpolate_gpu.cu:103 as nvcc contracts it
+        }
+        *reinterpret_cast<float4 *>(trow + o * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        if (c0 + lane < C) {
+            const uint64_t pol = l2_evict_first_policy();
+            bulk_store(out + ((long long)b * C + c0 + lane) * N + p0, smem_addr(tile + lane * FWD_LD),
+                       (uint32_t)npos * 4u, pol);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+}
+
+// grad_out (B,C,N), idx/weight (B,N,3) -> accT (B,M,C) += ; requires C % 4 == 0, N % 4 == 0
+__global__ void __launch_bounds__(256)
+interp_bwd_tma_kernel(int C, int N, int M, const float *__restrict__ grad_out, const int *__restrict__ idx,
+                      const float *__restrict__ weight, float *__restrict__ accT) {
+    extern __shared__ __align__(128) float tile[];   // rows at r*BWD_LD + 4*(r>>2); then idx, w
+    __shared__ __align__(8) uint64_t bar;
+    int *s_idx = reinterpret_cast<int *>(tile + TC * BWD_LD + 32);
+    float *s_w = reinterpret_cast<float *>(s_idx + TP * 3);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * TC;
+    const int p0 = blockIdx.x * TP;
+    const int npos = min(TP, N - p0);
+    const int rows = min(TC, C - c0);
+    const uint32_t bar_a = smem_addr(&bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 0) {
+        if (lane == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a),
+                         "r"((uint32_t)(rows * npos * 4))
+                         : "memory");
+        __syncwarp();
+        if (lane < rows) {
+            const uint64_t pol = l2_evict_first_policy();
+            bulk_load(smem_addr(tile + lane * BWD_LD + 4 * (lane >> 2)),
+                      grad_out + ((long long)b * C + c0 + lane) * N + p0, (uint32_t)npos * 4u, bar_a, pol);
+        }
+    }
+    const long long o3 = 3ll * ((long long)b * N + p0);
+    for (int i = threadIdx.x; i < npos * 3; i += 256) {
+        s_idx[i] = __ldg(idx + o3 + i);
+        s_w[i] = __ldg(weight + o3 + i);
+    }
+    __syncthreads();
+    {
+        uint32_t ok = 0;
+        while (!ok) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok)
+                : "r"(bar_a)
+                : "memory");
+        }
+    }
+    float *acc = accT + (long long)b * M * C + c0;
+    const int wbase = warp * 32;
+    const int wpos = min(32, npos - wbase);
+    const int j = lane >> 3, q = lane & 7;
+    const float *t0 = tile + (4 * q) * BWD_LD + 4 * q + wbase + j;
+    const bool cok = 4 * q < rows;
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+        if (o * 4 + j < wpos && cok) {
+            const int p = wbase + o * 4 + j;
+            const float g0 = t0[o * 4];
+            const float g1 = t0[o * 4 + BWD_LD];
+            const float g2 = t0[o * 4 + 2 * BWD_LD];
+            const float g3 = t0[o * 4 + 3 * BWD_LD];
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const float w = s_w[3 * p + u];
+                red_v4(acc + (long long)s_idx[3 * p + u] * C + 4 * q, __fmul_rn(g0, w), __fmul_rn(g1, w),
+                       __fmul_rn(g2, w), __fmul_rn(g3, w));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // direct kernels (no workspace / tiny C / P not a multiple of 8): one thread per position,
 // idx held in a register across the channel loop
 // ---------------------------------------------------------------------------------------
@@ -532,11 +659,21 @@ extern "C" int amc3d_gather_points_grad(int b, int c, int n, int npoints, const 
                         "gather_points_grad");
 }
 
-extern "C" int amc3d_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx,
-                                       const float *weight, float *out, void *stream) {
+static inline bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int amc3d_three_interpolate_ws(int b, int c, int m, int n, const float *points, const int *idx,
+                                          const float *weight, float *out, float *workspace, void *stream) {
     AMC3D_REQUIRE(b >= 0 && c >= 0 && m >= 0 && n >= 0, AMC3D_EINVAL, "three_interpolate: negative size");
     AMC3D_REQUIRE(b <= 65535, AMC3D_ELIMIT, "three_interpolate: batch %d > 65535", b);
     if (b == 0 || c == 0 || n == 0) return 0;
+    if (workspace != nullptr && c >= 8 && n % 4 == 0 && m > 0 && al16(out) && group_impl() >= 1) {
+        cudaStream_t st = as_stream(stream);
+        launch_transpose<false>(b, c, m, points, workspace, st);   // (B,C,m) -> (B,m,C)
+        dim3 grid(div_up(n, TP), div_up(c, TC), b);
+        const size_t smem = (TC * FWD_LD + TP * 6) * sizeof(float);
+        interp_fwd_tma_kernel<<<grid, 256, smem, st>>>(c, m, n, workspace, idx, weight, out);
+        return check_launch("three_interpolate");
+    }
     const int bx = div_up(n, 256);
     const int cchunk = pick_cchunk(c, (long long)bx * b);
     dim3 grid(bx, div_up(c, cchunk), b);
@@ -544,18 +681,38 @@ extern "C" int amc3d_three_interpolate(int b, int c, int m, int n, const float *
     return check_launch("three_interpolate");
 }
 
-extern "C" int amc3d_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out,
-                                            const int *idx, const float *weight, float *grad_points,
-                                            void *stream) {
+extern "C" int amc3d_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx,
+                                       const float *weight, float *out, void *stream) {
+    return amc3d_three_interpolate_ws(b, c, m, n, points, idx, weight, out, nullptr, stream);
+}
+
+extern "C" int amc3d_three_interpolate_grad_ws(int b, int c, int n, int m, const float *grad_out,
+                                               const int *idx, const float *weight, float *grad_points,
+                                               float *workspace, void *stream) {
     AMC3D_REQUIRE(b >= 0 && c >= 0 && m >= 0 && n >= 0, AMC3D_EINVAL, "three_interpolate_grad: negative size");
     AMC3D_REQUIRE(b <= 65535, AMC3D_ELIMIT, "three_interpolate_grad: batch %d > 65535", b);
     if (b == 0 || c == 0 || n == 0) return 0;
+    if (workspace != nullptr && c >= 8 && c % 4 == 0 && n % 4 == 0 && m > 0 && al16(grad_out) && group_impl() >= 1) {
+        cudaStream_t st = as_stream(stream);
+        cudaMemsetAsync(workspace, 0, sizeof(float) * (size_t)b * m * c, st);
+        dim3 grid(div_up(n, TP), div_up(c, TC), b);
+        const size_t smem = (TC * BWD_LD + 32 + TP * 6) * sizeof(float);
+        interp_bwd_tma_kernel<<<grid, 256, smem, st>>>(c, n, m, grad_out, idx, weight, workspace);
+        launch_transpose<true>(b, m, c, workspace, grad_points, st);   // (B,m,C) -> += (B,C,m)
+        return check_launch("three_interpolate_grad");
+    }
     const int bx = div_up(n, 256);
     const int cchunk = pick_cchunk(c, (long long)bx * b);
     dim3 grid(bx, div_up(c, cchunk), b);
     three_interp_grad_kernel<<<grid, 256, 0, as_stream(stream)>>>(c, n, m, cchunk, grad_out, idx, weight,
                                                                   grad_points);
     return check_launch("three_interpolate_grad");
+}
+
+extern "C" int amc3d_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out,
+                                            const int *idx, const float *weight, float *grad_points,
+                                            void *stream) {
+    return amc3d_three_interpolate_grad_ws(b, c, n, m, grad_out, idx, weight, grad_points, nullptr, stream);
 }
 
 extern "C" int amc3d_grouping_forward(int m, int nsample, int c, const float *input, const int *idx,

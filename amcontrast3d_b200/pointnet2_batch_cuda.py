@@ -81,12 +81,14 @@ def three_nn_wrapper(b, n, m, unknown, known, dist2, idx):
 def three_interpolate_wrapper(b, c, m, n, points, idx, weight, out):
     """ref: interpolate.cpp:31 three_interpolate_wrapper_fast"""
     with _guard(points):
-        _capi.call("amc3d_three_interpolate", b, c, m, n, ptr(points), ptr(idx), ptr(weight), ptr(out),
-                   stream(points))
+        ws = _workspace(points, b * m * c) if c >= 8 else None
+        _capi.call("amc3d_three_interpolate_ws", b, c, m, n, ptr(points), ptr(idx), ptr(weight), ptr(out),
+                   ptr(ws), stream(points))
 
 
 def three_interpolate_grad_wrapper(b, c, n, m, grad_out, idx, weight, grad_points):
     """ref: interpolate.cpp:45 three_interpolate_grad_wrapper_fast (grad_points pre-zeroed)"""
     with _guard(grad_out):
-        _capi.call("amc3d_three_interpolate_grad", b, c, n, m, ptr(grad_out), ptr(idx), ptr(weight),
-                   ptr(grad_points), stream(grad_out))
+        ws = _workspace(grad_out, b * m * c) if c >= 8 else None
+        _capi.call("amc3d_three_interpolate_grad_ws", b, c, n, m, ptr(grad_out), ptr(idx), ptr(weight),
+                   ptr(grad_points), ptr(ws), stream(grad_out))

@@ -187,10 +187,10 @@ def algorithmic_work(name, a):
     if name in ("amc3d_group_points_grad_ws", "amc3d_group_points_grad"):
         b, c, n, npnt, ns = a[:5]
         return "byte", 4.0 * b * (c * npnt * ns + 2 * c * n + npnt * ns)
-    if name == "amc3d_three_interpolate":
+    if name in ("amc3d_three_interpolate", "amc3d_three_interpolate_ws"):
         b, c, m, n = a[:4]
         return "byte", 4.0 * b * (c * n + c * m + 6 * n)
-    if name == "amc3d_three_interpolate_grad":
+    if name in ("amc3d_three_interpolate_grad", "amc3d_three_interpolate_grad_ws"):
         b, c, n, m = a[:4]
         return "byte", 4.0 * b * (c * n + 2 * c * m + 6 * n)
     return None, 0.0

@@ -99,11 +99,20 @@ int amc3d_three_nn(int b, int n, int m, const float *unknown, const float *known
  * ref: interpolate.cpp:31, interpolate_gpu.cu:107 */
 int amc3d_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx,
                             const float *weight, float *out, void *stream);
+/* Same, with a caller-provided workspace of b*m*c floats: the three neighbour rows of a position
+ * become three coalesced 128-byte reads of a channel-contiguous copy and the output leaves in
+ * bulk-async 1 KB rows.  NULL selects the direct kernel. */
+int amc3d_three_interpolate_ws(int b, int c, int m, int n, const float *points, const int *idx,
+                               const float *weight, float *out, float *workspace, void *stream);
 /* grad_points[b,c,idx[b,i,t]] += grad_out[b,c,i]*weight[b,i,t]; grad_points pre-zeroed.
  * ref: interpolate.cpp:45, interpolate_gpu.cu:152 */
 int amc3d_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out,
                                  const int *idx, const float *weight, float *grad_points,
                                  void *stream);
+/* Same, with a workspace of b*m*c floats (vector reductions into a channel-contiguous accumulator). */
+int amc3d_three_interpolate_grad_ws(int b, int c, int n, int m, const float *grad_out,
+                                    const int *idx, const float *weight, float *grad_points,
+                                    float *workspace, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * pointops family: packed (n,3) xyz / (n,c) features with cumulative i32 `offset` ends
