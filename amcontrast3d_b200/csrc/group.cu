@@ -174,8 +174,8 @@ __device__ __forceinline__ void bulk_load(uint32_t sdst, const void *gsrc, uint3
 }
 
 __global__ void __launch_bounds__(256)
-group_fwd_tma_kernel(int C, int N, int P, const float *__restrict__ srcT, const int *__restrict__ idx,
-                     float *__restrict__ out) {
+group_fwd_tma_kernel(int C, int N, int P, int nsample, const float *__restrict__ srcT,
+                     const int *__restrict__ idx, float *__restrict__ out) {
     extern __shared__ __align__(128) float tile[];   // [TC][FWD_LD]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.z;
@@ -188,7 +188,16 @@ group_fwd_tma_kernel(int C, int N, int P, const float *__restrict__ srcT, const 
     const int wpos = min(32, npos - warp * 32);       // positions of this warp (may be <= 0)
     float *trow = tile + lane * FWD_LD + warp * 32;
     if (wpos == 32) {
-        // full warp tile: two batches of 16 independent gathers in flight per lane
+        // full warp tile: two batches of 16 independent gathers in flight per lane.  Slots that repeat
+        // the first index of their query (ball_query's padding, ~40 % of all slots) reuse its value
+        // instead of issuing another load (nsample % 32 == 0: the warp lies inside one query).
+        int i_first = -1;
+        float v_first = 0.f;
+        if (nsample > 0) {
+            const long long gp0 = (long long)p0 + warp * 32;
+            i_first = __ldg(idx + (long long)b * P + gp0 / nsample * nsample);
+            v_first = __ldg(src + (long long)i_first * C);
+        }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             int4 ii[4];
@@ -197,10 +206,10 @@ group_fwd_tma_kernel(int C, int N, int P, const float *__restrict__ srcT, const 
             for (int o = 0; o < 4; ++o) ii[o] = __ldg(reinterpret_cast<const int4 *>(ip + h * 16 + o * 4));
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
-                v[o].x = __ldg(src + (long long)ii[o].x * C);
-                v[o].y = __ldg(src + (long long)ii[o].y * C);
-                v[o].z = __ldg(src + (long long)ii[o].z * C);
-                v[o].w = __ldg(src + (long long)ii[o].w * C);
+                v[o].x = ii[o].x == i_first ? v_first : __ldg(src + (long long)ii[o].x * C);
+                v[o].y = ii[o].y == i_first ? v_first : __ldg(src + (long long)ii[o].y * C);
+                v[o].z = ii[o].z == i_first ? v_first : __ldg(src + (long long)ii[o].z * C);
+                v[o].w = ii[o].w == i_first ? v_first : __ldg(src + (long long)ii[o].w * C);
             }
 #pragma unroll
             for (int o = 0; o < 4; ++o) *reinterpret_cast<float4 *>(trow + h * 16 + o * 4) = v[o];
@@ -236,8 +245,8 @@ __device__ __forceinline__ void red_v4(float *p, float a, float b, float c, floa
 // grad_out (B,C,P), idx (B,P) -> accT (B,N,C) +=.  V4: vector reductions (needs C % 4 == 0)
 template <bool V4>
 __global__ void __launch_bounds__(256)
-group_bwd_tma_kernel(int C, int N, int P, const float *__restrict__ grad_out, const int *__restrict__ idx,
-                     float *__restrict__ accT) {
+group_bwd_tma_kernel(int C, int N, int P, int nsample, const float *__restrict__ grad_out,
+                     const int *__restrict__ idx, float *__restrict__ accT) {
     extern __shared__ __align__(128) float tile[];   // rows at r*BWD_LD + 4*(r>>2)
     __shared__ __align__(8) uint64_t bar;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -287,14 +296,52 @@ group_bwd_tma_kernel(int C, int N, int P, const float *__restrict__ grad_out, co
         const int j = lane >> 3, q = lane & 7;
         const float *t0 = tile + (4 * q) * BWD_LD + 4 * q + wbase + j;
         const bool cok = 4 * q < rows;                 // C % 4 == 0: whole quads only
+        // Positions that repeat the first index of their query (ball_query pads a row with its first
+        // hit: ~40 % of all slots at PointNeXt's radii) are summed in registers and leave as ONE
+        // reduction — the L2 atomic units are what bounds this kernel.  Valid for any idx: equal
+        // indices are the same target.  Needs nsample % 32 == 0 so that a warp stays inside one query.
+        uint32_t dup = 0;
+        int keep = -1;
+        if (nsample > 0) {
+            const long long gp0 = (long long)p0 + wbase;
+            const long long fp = gp0 / nsample * nsample;
+            int first_idx = __shfl_sync(0xffffffffu, my_idx, 0);
+            if (fp != gp0) first_idx = __ldg(idx + (long long)b * P + fp);
+            const uint32_t same = __ballot_sync(0xffffffffu, lane < wpos && my_idx == first_idx);
+            if (same & (same - 1)) {
+                keep = __ffs(same) - 1;
+                dup = same & ~(1u << keep);
+            }
+        }
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if (dup != 0) {
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+                if (((dup >> (o * 4 + j)) & 1u) && cok) {
+                    a0 += t0[o * 4];
+                    a1 += t0[o * 4 + BWD_LD];
+                    a2 += t0[o * 4 + 2 * BWD_LD];
+                    a3 += t0[o * 4 + 3 * BWD_LD];
+                }
+            }
+#pragma unroll
+            for (int x = 8; x <= 16; x <<= 1) {
+                a0 += __shfl_xor_sync(0xffffffffu, a0, x);
+                a1 += __shfl_xor_sync(0xffffffffu, a1, x);
+                a2 += __shfl_xor_sync(0xffffffffu, a2, x);
+                a3 += __shfl_xor_sync(0xffffffffu, a3, x);
+            }
+        }
 #pragma unroll
         for (int o = 0; o < 8; ++o) {
-            const int pi = __shfl_sync(0xffffffffu, my_idx, o * 4 + j);
-            if (o * 4 + j < wpos && cok) {
-                const float g0 = t0[o * 4];
-                const float g1 = t0[o * 4 + BWD_LD];
-                const float g2 = t0[o * 4 + 2 * BWD_LD];
-                const float g3 = t0[o * 4 + 3 * BWD_LD];
+            const int pp = o * 4 + j;
+            const int pi = __shfl_sync(0xffffffffu, my_idx, pp);
+            if (pp < wpos && cok && !((dup >> pp) & 1u)) {
+                float g0 = t0[o * 4];
+                float g1 = t0[o * 4 + BWD_LD];
+                float g2 = t0[o * 4 + 2 * BWD_LD];
+                float g3 = t0[o * 4 + 3 * BWD_LD];
+                if (pp == keep) { g0 += a0; g1 += a1; g2 += a2; g3 += a3; }
                 red_v4(acc + (long long)pi * C + 4 * q, g0, g1, g2, g3);
             }
         }
@@ -582,7 +629,7 @@ static int group_impl() {
 }
 
 static int group_common(bool fwd, int b, int c, int n, long long P, const float *src, const int *idx,
-                        float *dst, float *workspace, cudaStream_t st, const char *what) {
+                        float *dst, float *workspace, cudaStream_t st, const char *what, int nsample = 0) {
     if (b == 0 || c == 0 || P == 0) return 0;
     AMC3D_REQUIRE(b <= 65535, AMC3D_ELIMIT, "%s: batch %d > 65535", what, b);
     AMC3D_REQUIRE(P < (1ll << 31), AMC3D_ELIMIT, "%s: npoints*nsample too large", what);
@@ -591,19 +638,21 @@ static int group_common(bool fwd, int b, int c, int n, long long P, const float 
     if (workspace != nullptr && c >= 8 && aligned && n > 0) {
         dim3 grid((unsigned)div_up_ll(P, GRP_WARPS * 32), div_up(c, 32), b);
         const int impl = group_impl();
+        static const bool no_combine = getenv("AMC3D_GROUP_NOCOMBINE") != nullptr;   // for measurements
+        const int combine = (!no_combine && nsample >= 32 && nsample % 32 == 0) ? nsample : 0;
         if (fwd) {
             launch_transpose<false>(b, c, n, src, workspace, st);  // (B,C,N) -> (B,N,C)
             if (impl >= 1)
-                group_fwd_tma_kernel<<<grid, 256, TC * FWD_LD * sizeof(float), st>>>(c, n, (int)P, workspace, idx, dst);
+                group_fwd_tma_kernel<<<grid, 256, TC * FWD_LD * sizeof(float), st>>>(c, n, (int)P, combine, workspace, idx, dst);
             else
                 group_fwd_cl_kernel<<<grid, GRP_WARPS * 32, 0, st>>>(c, n, (int)P, workspace, idx, dst);
         } else {
             cudaMemsetAsync(workspace, 0, sizeof(float) * (size_t)b * n * c, st);
             const size_t smem = (TC * BWD_LD + 32) * sizeof(float);
             if (impl >= 2 && c % 4 == 0)
-                group_bwd_tma_kernel<true><<<grid, 256, smem, st>>>(c, n, (int)P, src, idx, workspace);
+                group_bwd_tma_kernel<true><<<grid, 256, smem, st>>>(c, n, (int)P, combine, src, idx, workspace);
             else if (impl >= 1)
-                group_bwd_tma_kernel<false><<<grid, 256, smem, st>>>(c, n, (int)P, src, idx, workspace);
+                group_bwd_tma_kernel<false><<<grid, 256, smem, st>>>(c, n, (int)P, 0, src, idx, workspace);
             else
                 group_bwd_cl_kernel<<<grid, GRP_WARPS * 32, 0, st>>>(c, n, (int)P, src, idx, workspace);
             launch_transpose<true>(b, n, c, workspace, dst, st);   // (B,N,C) -> += (B,C,N)
@@ -625,7 +674,7 @@ extern "C" int amc3d_group_points_ws(int b, int c, int n, int npoints, int nsamp
     AMC3D_REQUIRE(b >= 0 && c >= 0 && n >= 0 && npoints >= 0 && nsample >= 0, AMC3D_EINVAL,
                   "group_points: negative size");
     return group_common(true, b, c, n, (long long)npoints * nsample, points, idx, out, workspace,
-                        as_stream(stream), "group_points");
+                        as_stream(stream), "group_points", nsample);
 }
 extern "C" int amc3d_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
                                   const int *idx, float *out, void *stream) {
@@ -638,7 +687,7 @@ extern "C" int amc3d_group_points_grad_ws(int b, int c, int n, int npoints, int 
     AMC3D_REQUIRE(b >= 0 && c >= 0 && n >= 0 && npoints >= 0 && nsample >= 0, AMC3D_EINVAL,
                   "group_points_grad: negative size");
     return group_common(false, b, c, n, (long long)npoints * nsample, grad_out, idx, grad_points,
-                        workspace, as_stream(stream), "group_points_grad");
+                        workspace, as_stream(stream), "group_points_grad", nsample);
 }
 extern "C" int amc3d_group_points_grad(int b, int c, int n, int npoints, int nsample,
                                        const float *grad_out, const int *idx, float *grad_points,
