@@ -328,23 +328,29 @@ struct WarpList {
     }
 };
 
-// smallest T with  #{distances <= T} >= k  over the 4 x 32 values held by the warp (radix
-// select on the bit pattern: non-negative floats order like their bits)
-__device__ __forceinline__ float warp_kth_of_128(const float (&dd)[4], int k) {
-    uint32_t bitsv[4];
+// An upper bound T of the k-th smallest of the 4 x 32 distances held by the warp, tight to 2^-7
+// relative: radix select on the bit pattern (non-negative floats order like their bits) over bits
+// 30..17, two bits per step — the counts for the three candidate prefixes travel in one packed
+// REDUX.SUM (each count <= 128 fits a byte) — and the 17 low bits rounded up.  #{d <= T} >= k always;
+// the handful of extra candidates a looser T lets through fall off the end of the sorted list.
+__device__ __forceinline__ float warp_kth_bound_of_128(const float (&dd)[4], int k) {
+    uint32_t v[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) bitsv[r] = __float_as_uint(dd[r]);
+    for (int r = 0; r < 4; ++r) v[r] = __float_as_uint(dd[r]);
     uint32_t T = 0;
-#pragma unroll 1
-    for (int b = 30; b >= 0; --b) {
-        const uint32_t cand = T | (1u << b);
-        int c = 0;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) c += bitsv[r] < cand ? 1 : 0;
+    for (int b = 29; b >= 17; b -= 2) {
+        const uint32_t t1 = T | (1u << b), t2 = T | (2u << b), t3 = T | (3u << b);
+        uint32_t c = 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            c += (v[r] < t1 ? 1u : 0u) + (v[r] < t2 ? 0x100u : 0u) + (v[r] < t3 ? 0x10000u : 0u);
         c = __reduce_add_sync(0xffffffffu, c);
-        if (c < k) T = cand;       // fewer than k values below cand: the k-th is >= cand
+        const int c1 = c & 0xff, c2 = (c >> 8) & 0xff, c3 = c >> 16;
+        // fewer than k values below a prefix: the k-th is >= that prefix
+        T = c3 < k ? t3 : (c2 < k ? t2 : (c1 < k ? t1 : T));
     }
-    return __uint_as_float(T);
+    return __uint_as_float(T | 0x1ffffu);
 }
 
 // geometry of a batched, tile-aligned sorted point set
@@ -397,9 +403,20 @@ knn_wq_kernel(Geom gs, int m, int mpad, int nsample, int self, int qpw, const fl
                 }
             }
             if (first) {
-                // bulk seed: only the ~k nearest of the first tile go through the insertion
-                td = fminf(warp_kth_of_128(dd, min(nsample, GT)), KG_INIT);
-                ti = 0x7fffffff;
+                // bulk seed: only the ~k nearest of the first tile go through the insertion, and
+                // without the per-insert threshold refresh (an entry beyond the k-th falls off the list)
+                td = fminf(warp_kth_bound_of_128(dd, min(nsample, GT)), KG_INIT);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    uint32_t mask = __ballot_sync(0xffffffffu, dd[r] <= td);
+                    while (mask) {
+                        const int bl = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        best.insert(__shfl_sync(0xffffffffu, dd[r], bl), __shfl_sync(0xffffffffu, oi[r], bl), lane);
+                    }
+                }
+                best.threshold(td, ti);
+                return;
             }
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
@@ -413,13 +430,12 @@ knn_wq_kernel(Geom gs, int m, int mpad, int nsample, int self, int qpw, const fl
                     float nd;
                     int ni;
                     best.threshold(nd, ni);
-                    // while seeding, the provisional (T, INT_MAX) bound stays until the list is full
-                    if (!first || nd < KG_INIT) { td = nd; ti = ni; }
+                    td = nd;
+                    ti = ni;
                     cand = cand && lane != bl && lex_lt(dd[r], oi[r], td, ti);
                     mask = __ballot_sync(0xffffffffu, cand);
                 }
             }
-            if (first) best.threshold(td, ti);
         };
 
         // ---- the tile at the query's own position and its two neighbours first -------------
