@@ -99,17 +99,21 @@ class GradBuckets:
         self.stream = torch.cuda.Stream(device=device) if torch.device(device).type == "cuda" else None
         self._work = []
 
-    def launch(self):
-        """Issue the all-reduces (averaging by world size afterwards is left to the optimizer step)."""
+    def launch(self, first: int = 0, last: int | None = None):
+        """Issue the all-reduces of buckets [first, last) (averaging by world size afterwards is left to
+        the optimizer step).  DDP's buckets become ready one after another during the backward, so all but
+        the last overlap compute; a caller that replays the step as one CUDA graph models that by
+        launching buckets [0, n-1) before the replay and bucket n-1 after it."""
         if not (dist.is_initialized() and dist.get_world_size() > 1):
             return
+        todo = self.buckets[first:last]
         if self.stream is not None:
             self.stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.stream):
-                for b in self.buckets:
+                for b in todo:
                     self._work.append(dist.all_reduce(b, op=dist.ReduceOp.SUM, async_op=True))
         else:
-            for b in self.buckets:
+            for b in todo:
                 self._work.append(dist.all_reduce(b, op=dist.ReduceOp.SUM, async_op=True))
 
     def wait(self):
