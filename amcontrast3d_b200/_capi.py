@@ -88,7 +88,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     with _lock:
         if _lib is not None:
             return _lib
-        path = _build.LIBPATH
+        path = os.environ.get("AMC3D_LIB") or _build.LIBPATH      # AMC3D_LIB: an experimental build of the same ABI
         if not os.path.exists(path):
             if not build_if_missing:
                 raise Amc3dError(f"{path} is missing: run `python -m amcontrast3d_b200._build`")

@@ -36,7 +36,11 @@
 
 namespace amc3d {
 
-constexpr int GT = 128;                 // threads per CTA == points per tile
+#ifndef AMC3D_GT
+#define AMC3D_GT 128
+#endif
+constexpr int GT = AMC3D_GT;            // points per tile (32, 64 or 128)
+constexpr int GR = GT / 32;             // rounds of 32 lanes per tile
 constexpr float KG_INIT = 1e10f;
 constexpr float KG_SAFE = 1.0f - 1.0f / 8192.0f;
 
@@ -333,17 +337,17 @@ struct WarpList {
 // 30..17, two bits per step — the counts for the three candidate prefixes travel in one packed
 // REDUX.SUM (each count <= 128 fits a byte) — and the 17 low bits rounded up.  #{d <= T} >= k always;
 // the handful of extra candidates a looser T lets through fall off the end of the sorted list.
-__device__ __forceinline__ float warp_kth_bound_of_128(const float (&dd)[4], int k) {
-    uint32_t v[4];
+__device__ __forceinline__ float warp_kth_bound_of_128(const float (&dd)[GR], int k) {
+    uint32_t v[GR];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) v[r] = __float_as_uint(dd[r]);
+    for (int r = 0; r < GR; ++r) v[r] = __float_as_uint(dd[r]);
     uint32_t T = 0;
 #pragma unroll
     for (int b = 29; b >= 17; b -= 2) {
         const uint32_t t1 = T | (1u << b), t2 = T | (2u << b), t3 = T | (3u << b);
         uint32_t c = 0;
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+        for (int r = 0; r < GR; ++r)
             c += (v[r] < t1 ? 1u : 0u) + (v[r] < t2 ? 0x100u : 0u) + (v[r] < t3 ? 0x10000u : 0u);
         c = __reduce_add_sync(0xffffffffu, c);
         const int c1 = c & 0xff, c2 = (c >> 8) & 0xff, c3 = c >> 16;
@@ -388,10 +392,10 @@ knn_wq_kernel(Geom gs, int m, int mpad, int nsample, int self, int qpw, const fl
 
         // evaluate the 128 points of global tile t against this query; first=true seeds the list
         auto process_tile = [&](int t, bool first) {
-            float dd[4];
-            int oi[4];
+            float dd[GR];
+            int oi[GR];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
+            for (int r = 0; r < GR; ++r) {
                 const int l = (t - tb0) * GT + r * 32 + lane;  // position within the cloud
                 if (l < n) {
                     const float4 p = __ldg(sp + (long long)t * GT + r * 32 + lane);
@@ -407,7 +411,7 @@ knn_wq_kernel(Geom gs, int m, int mpad, int nsample, int self, int qpw, const fl
                 // without the per-insert threshold refresh (an entry beyond the k-th falls off the list)
                 td = fminf(warp_kth_bound_of_128(dd, min(nsample, GT)), KG_INIT);
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
+                for (int r = 0; r < GR; ++r) {
                     uint32_t mask = __ballot_sync(0xffffffffu, dd[r] <= td);
                     while (mask) {
                         const int bl = __ffs(mask) - 1;
@@ -419,7 +423,7 @@ knn_wq_kernel(Geom gs, int m, int mpad, int nsample, int self, int qpw, const fl
                 return;
             }
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
+            for (int r = 0; r < GR; ++r) {
                 bool cand = dd[r] <= td && lex_lt(dd[r], oi[r], td, ti);
                 uint32_t mask = __ballot_sync(0xffffffffu, cand);
                 while (mask) {
@@ -543,7 +547,7 @@ ball_wq_kernel(Geom gs, int m, int mpad, float radius, int nsample, int self, in
 
         auto process_tile = [&](int t) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
+            for (int r = 0; r < GR; ++r) {
                 const int l = (t - tb0) * GT + r * 32 + lane;
                 bool cand = false;
                 int oi = 0x7fffffff;

@@ -175,6 +175,12 @@ class PathReplay:
         Returns self; afterwards step_graph() replays it."""
         from . import _capi
         assert _capi.PROFILE is None, "do not capture while per-call profiling is on"
+        # the leaves' AccumulateGrad nodes were created on the default stream by earlier eager steps; the
+        # capture stream differs by construction, which is harmless here (everything is ordered by the
+        # capture) — silence torch's per-step warning about it
+        quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if quiet is not None:
+            quiet(False)
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):            # warm-up off the default stream, as torch requires
