@@ -26,12 +26,13 @@ def _stage_ambiguity(n, i, stageACE_list, target, num_classes, ignore_index, amb
         p = p.float()
     nsample = int(ambiguity_args.nsample)
     cls, _ = stage_label_ids(n, i, stageACE_list, target, nstride, num_classes, ignore_index)
-    knn_idx, _ = _amloss.knn_raw(nsample, p, p, o, o)
+    knn_idx, _, order = _amloss.knn_raw(nsample, p, p, o, o, want_order=True)
     nl = _amloss.NeighbourList(knn_idx, drop_self=True)       # the reference's [..., 1:] without the copy
     posbits, cnt, max_cnt = _amloss.posmask_count(nl, cls)
     a, stats = _amloss.ambiguity(p, nl, posbits, cnt, max_cnt, ambiguity_args.cctype, ambiguity_args.ccbeta,
                                  ambiguity_args.nu)
-    return dict(p=p, features=features, nl=nl, posbits=posbits, cnt=cnt, a=a, stats=stats, knn_idx=knn_idx, cls=cls)
+    return dict(p=p, features=features, nl=nl, posbits=posbits, cnt=cnt, a=a, stats=stats, knn_idx=knn_idx, cls=cls,
+                order=order)
 
 
 class AmbiguityHead(nn.Module):
@@ -128,7 +129,7 @@ class ContrastHead(nn.Module):
         output_ai = stageACE_list['ambiguity'][i].flatten() if 'ambiguity' in stageACE_list.keys() else None
         features = st['features']
         if _amloss.fused_supported(ambiguity_args):
-            loss = _amloss.am_loss(features, st['nl'], st['posbits'], a, st['stats'], ambiguity_args)
+            loss = _amloss.am_loss(features, st['nl'], st['posbits'], a, st['stats'], ambiguity_args, st['order'])
         else:
             # torch composition on device over the same kNN / posmask / ambiguity
             sel = torch.logical_and(0 < a, a <= 1)

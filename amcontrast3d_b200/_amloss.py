@@ -22,8 +22,10 @@ def _i32(t):
     return t if t.dtype == torch.int32 else t.int()
 
 
-def knn_raw(nsample: int, xyz, new_xyz, offset, new_offset):
-    """amc3d_knnquery -> (idx (m,nsample) i32, dist2 (m,nsample) f32 SQUARED); no sqrt, no autograd."""
+def knn_raw(nsample: int, xyz, new_xyz, offset, new_offset, want_order: bool = False):
+    """amc3d_knnquery -> (idx (m,nsample) i32, dist2 (m,nsample) f32 SQUARED); no sqrt, no autograd.
+    want_order=True additionally returns the spatially coherent query permutation (m) i32 of
+    amc3d_knnquery_order, which the fused loss uses as its anchor order."""
     if new_xyz is None:
         new_xyz = xyz
     assert xyz.is_contiguous() and new_xyz.is_contiguous()
@@ -32,9 +34,12 @@ def knn_raw(nsample: int, xyz, new_xyz, offset, new_offset):
     idx = torch.empty((m, nsample), dtype=torch.int32, device=xyz.device)
     dist2 = torch.empty((m, nsample), dtype=torch.float32, device=xyz.device)
     offset, new_offset = _i32(offset).contiguous(), _i32(new_offset).contiguous()
+    order = torch.empty((m,), dtype=torch.int32, device=xyz.device) if want_order else None
     with _capi.guard(xyz):
-        _capi.call("amc3d_knnquery", int(xyz.shape[0]), m, int(offset.shape[0]), nsample, ptr(xyz), ptr(new_xyz),
-                   ptr(offset), ptr(new_offset), ptr(idx), ptr(dist2), stream(xyz))
+        _capi.call("amc3d_knnquery_order", int(xyz.shape[0]), m, int(offset.shape[0]), nsample, ptr(xyz), ptr(new_xyz),
+                   ptr(offset), ptr(new_offset), ptr(idx), ptr(dist2), ptr(order), stream(xyz))
+    if want_order:
+        return idx, dist2, order
     return idx, dist2
 
 
@@ -132,7 +137,7 @@ class AMLossFunction(Function):
     scalar and |sel| from device memory — no host synchronisation anywhere."""
 
     @staticmethod
-    def forward(ctx, f, nl: NeighbourList, posbits, a, stats, params: LossParams):
+    def forward(ctx, f, nl: NeighbourList, posbits, a, stats, params: LossParams, order=None):
         assert f.is_contiguous() and f.dtype == torch.float32 and f.dim() == 2
         m, d = f.shape
         dev = f.device
@@ -143,8 +148,8 @@ class AMLossFunction(Function):
         with _capi.guard(f):
             st = stream(f)
             _capi.call("amc3d_row_inv_norm", m, d, ptr(f), ptr(inv), st)
-            _capi.call("amc3d_amloss_forward", m, d, nl.ke, nl.ld, ptr(f), ptr(inv), nl.ptr, ptr(posbits), ptr(a),
-                       ctypes.byref(params), ptr(loss_pt), ptr(ghat), st)
+            _capi.call("amc3d_amloss_forward_order", m, d, nl.ke, nl.ld, ptr(f), ptr(inv), nl.ptr, ptr(posbits),
+                       ptr(a), ctypes.byref(params), ptr(loss_pt), ptr(ghat), ptr(order), st)
             _capi.call("amc3d_amloss_reduce", m, ptr(loss_pt), ptr(stats), ptr(loss), st)
         ctx.save_for_backward(f, inv, ghat, stats)
         ctx.loss_rows = loss_pt
@@ -159,14 +164,14 @@ class AMLossFunction(Function):
         with _capi.guard(f):
             _capi.call("amc3d_amloss_backward", m, d, ptr(f), ptr(inv), ptr(ghat), ptr(up), ptr(stats), 0,
                        ptr(grad_f), stream(f))
-        return grad_f, None, None, None, None, None
+        return grad_f, None, None, None, None, None, None
 
 
-def am_loss(f, nl, posbits, a, stats, args):
+def am_loss(f, nl, posbits, a, stats, args, order=None):
     f = f.contiguous()
     if f.dtype != torch.float32:
         f = f.float()
-    return AMLossFunction.apply(f, nl, posbits, a, stats, loss_params(args))
+    return AMLossFunction.apply(f, nl, posbits, a, stats, loss_params(args), order)
 
 
 # --------------------------------------------------------------------------------------------

@@ -56,6 +56,7 @@ SIGNATURES = {
     "amc3d_three_interpolate_ws": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "amc3d_three_interpolate_grad_ws": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "amc3d_knnquery": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "amc3d_knnquery_order": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "amc3d_grouping_forward": [_I, _I, _I, _P, _P, _P, _P],
     "amc3d_grouping_backward": [_I, _I, _I, _P, _P, _P, _P],
     "amc3d_stage_labels": [_I, _I, _I, _I, _LL, _P, _P, _P, _P],
@@ -63,6 +64,7 @@ SIGNATURES = {
     "amc3d_ambiguity": [_I, _I, _I, _P, _P, _P, _P, _P, _I, _F, _F, _P, _P, _P],
     "amc3d_row_inv_norm": [_I, _I, _P, _P, _P],
     "amc3d_amloss_forward": [_I, _I, _I, _I, _P, _P, _P, _P, _P, POINTER(LossParams), _P, _P, _P],
+    "amc3d_amloss_forward_order": [_I, _I, _I, _I, _P, _P, _P, _P, _P, POINTER(LossParams), _P, _P, _P, _P],
     "amc3d_amloss_reduce": [_I, _P, _P, _P, _P],
     "amc3d_amloss_backward": [_I, _I, _P, _P, _P, _P, _P, _I, _P, _P],
     "amc3d_refine_select": [_I, _I, _I, _P, _P, _P, _P],

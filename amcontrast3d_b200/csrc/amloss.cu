@@ -208,14 +208,16 @@ __global__ void __launch_bounds__(256)
 amloss_forward_kernel(int m, int ke, int ld, const float *__restrict__ f, const float *__restrict__ inv,
                       const int *__restrict__ nbr, const uint32_t *__restrict__ posbits,
                       const float *__restrict__ a, amc3d_loss_params prm, float *__restrict__ loss_pt,
-                      float *__restrict__ ghat) {
+                      float *__restrict__ ghat, const int *__restrict__ order) {
     constexpr int D4 = G * V;   // float4 chunks per row
     constexpr int D = D4 * 4;
     const int g = threadIdx.x % G;
-    const long long i = ((long long)blockIdx.x * 256 + threadIdx.x) / G;
+    const long long slot = ((long long)blockIdx.x * 256 + threadIdx.x) / G;
     // all lanes of a group share i; whole groups exit together.  Shuffles below use the full
     // mask, so a partially filled last warp keeps its idle groups alive until the end.
-    const bool in_range = i < m;
+    const bool in_range = slot < m;
+    // anchors are visited in `order` (spatially coherent): neighbouring groups then gather the same rows
+    const long long i = (in_range && order != nullptr) ? __ldg(order + slot) : slot;
     const float ai = in_range ? __ldg(a + i) : 0.f;
     const bool sel = in_range && (0.f < ai) && (ai <= 1.f);
     if (in_range && !sel && g == 0) loss_pt[i] = 0.f;
@@ -562,27 +564,34 @@ extern "C" int amc3d_row_inv_norm(int m, int d, const float *f, float *inv, void
 template <int G, int V>
 static void launch_fwd(int m, int ke, int ld, const float *f, const float *inv, const int *nbr,
                        const uint32_t *posbits, const float *a, const amc3d_loss_params &prm,
-                       float *loss_pt, float *ghat, cudaStream_t st) {
+                       float *loss_pt, float *ghat, const int *order, cudaStream_t st) {
     const long long threads = (long long)m * G;
     amloss_forward_kernel<G, V><<<(unsigned)div_up_ll(threads, 256), 256, 0, st>>>(m, ke, ld, f, inv, nbr, posbits,
-                                                                                    a, prm, loss_pt, ghat);
+                                                                                    a, prm, loss_pt, ghat, order);
 }
 
 extern "C" int amc3d_amloss_forward(int m, int d, int ke, int ld, const float *f, const float *inv,
                                     const int *nbr, const uint32_t *posbits, const float *a,
                                     const amc3d_loss_params *params, float *loss_pt, float *ghat,
                                     void *stream) {
+    return amc3d_amloss_forward_order(m, d, ke, ld, f, inv, nbr, posbits, a, params, loss_pt, ghat, nullptr, stream);
+}
+
+extern "C" int amc3d_amloss_forward_order(int m, int d, int ke, int ld, const float *f, const float *inv,
+                                          const int *nbr, const uint32_t *posbits, const float *a,
+                                          const amc3d_loss_params *params, float *loss_pt, float *ghat,
+                                          const int *order, void *stream) {
     AMC3D_REQUIRE(m >= 0 && d >= 1 && ke >= 1 && ke <= KE_MAX && ld >= ke, AMC3D_EINVAL, "amloss_forward: bad sizes m=%d d=%d ke=%d ld=%d", m, d, ke, ld);
     AMC3D_REQUIRE(params != nullptr, AMC3D_EINVAL, "amloss_forward: params is NULL");
     AMC3D_REQUIRE(params->cl_method == 1 || params->cl_method == 2, AMC3D_EINVAL, "amloss_forward: cl_method=%d", params->cl_method);
     if (m == 0) return 0;
     cudaStream_t st = as_stream(stream);
     const bool al = ((reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(ghat)) & 15) == 0;
-    if (al && d == 32) launch_fwd<8, 1>(m, ke, ld, f, inv, nbr, posbits, a, *params, loss_pt, ghat, st);
-    else if (al && d == 64) launch_fwd<16, 1>(m, ke, ld, f, inv, nbr, posbits, a, *params, loss_pt, ghat, st);
-    else if (al && d == 128) launch_fwd<32, 1>(m, ke, ld, f, inv, nbr, posbits, a, *params, loss_pt, ghat, st);
-    else if (al && d == 256) launch_fwd<32, 2>(m, ke, ld, f, inv, nbr, posbits, a, *params, loss_pt, ghat, st);
-    else if (al && d == 512) launch_fwd<32, 4>(m, ke, ld, f, inv, nbr, posbits, a, *params, loss_pt, ghat, st);
+    if (al && d == 32) launch_fwd<8, 1>(m, ke, ld, f, inv, nbr, posbits, a, *params, loss_pt, ghat, order, st);
+    else if (al && d == 64) launch_fwd<16, 1>(m, ke, ld, f, inv, nbr, posbits, a, *params, loss_pt, ghat, order, st);
+    else if (al && d == 128) launch_fwd<32, 1>(m, ke, ld, f, inv, nbr, posbits, a, *params, loss_pt, ghat, order, st);
+    else if (al && d == 256) launch_fwd<32, 2>(m, ke, ld, f, inv, nbr, posbits, a, *params, loss_pt, ghat, order, st);
+    else if (al && d == 512) launch_fwd<32, 4>(m, ke, ld, f, inv, nbr, posbits, a, *params, loss_pt, ghat, order, st);
     else
         amloss_forward_generic_kernel<<<div_up(m, 8), 256, 0, st>>>(m, d, ke, ld, f, inv, nbr, posbits, a, *params,
                                                                     loss_pt, ghat);

@@ -194,7 +194,7 @@ three_nn_kernel(int n, int m, const float *__restrict__ unknown, const float *__
 
 // knn_grid.cu: the same searches with spatial culling (identical results)
 int knn_grid_batched(int nb, int n, int m, int nsample, const float *xyz, const float *new_xyz, int *idx,
-                     float *dist2, cudaStream_t st);
+                     float *dist2, cudaStream_t st, int *order_out = nullptr);
 int ball_grid_batched(int nb, int n, int m, float radius, int nsample, const float *xyz, const float *new_xyz,
                       int *idx, cudaStream_t st);
 

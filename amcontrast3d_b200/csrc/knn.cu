@@ -253,7 +253,12 @@ static void launch_reg(bool check, int blocks, cudaStream_t st, int n, int m, in
 }
 
 int knn_grid_single_segment(int n, int m, int nsample, const float *xyz, const float *new_xyz, int *idx,
-                            float *dist2, cudaStream_t st);   // knn_grid.cu
+                            float *dist2, cudaStream_t st, int *order_out);   // knn_grid.cu
+
+__global__ void iota_kernel(int m, int *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) out[i] = i;
+}
 
 }  // namespace amc3d
 
@@ -272,6 +277,12 @@ static bool force_brute() {
 extern "C" int amc3d_knnquery(int n, int m, int nseg, int nsample, const float *xyz,
                               const float *new_xyz, const int *offset, const int *new_offset,
                               int *idx, float *dist2, void *stream) {
+    return amc3d_knnquery_order(n, m, nseg, nsample, xyz, new_xyz, offset, new_offset, idx, dist2, nullptr, stream);
+}
+
+extern "C" int amc3d_knnquery_order(int n, int m, int nseg, int nsample, const float *xyz,
+                                    const float *new_xyz, const int *offset, const int *new_offset,
+                                    int *idx, float *dist2, int *order, void *stream) {
     AMC3D_REQUIRE(n >= 0 && m >= 0 && nseg >= 1 && nsample >= 1, AMC3D_EINVAL,
                   "knnquery: bad sizes n=%d m=%d nseg=%d nsample=%d", n, m, nseg, nsample);
     AMC3D_REQUIRE(nsample <= 128, AMC3D_ELIMIT, "knnquery: nsample=%d > 128", nsample);
@@ -280,13 +291,14 @@ extern "C" int amc3d_knnquery(int n, int m, int nseg, int nsample, const float *
     // One segment (offset = [n], new_offset = [m] — what AMContrast3D always passes): exact search with
     // spatial culling.  Small problems are not worth the sort.
     if (nseg == 1 && n >= 2048 && !force_brute()) {
-        const int rc = knn_grid_single_segment(n, m, nsample, xyz, new_xyz, idx, dist2, st);
+        const int rc = knn_grid_single_segment(n, m, nsample, xyz, new_xyz, idx, dist2, st, order);
         if (rc != 0) {
             set_error("knnquery (grid): %s", cudaGetErrorString((cudaError_t)rc));
             return rc;
         }
         return check_launch("knnquery");
     }
+    if (order != nullptr) iota_kernel<<<div_up(m, 256), 256, 0, st>>>(m, order);   // brute force visits in index order
     // A single segment (the AMContrast3D case: offset = [B*n]) never needs the per-candidate
     // range check; with several segments a CTA may straddle a boundary, so check.
     const bool check = nseg > 1;

@@ -372,7 +372,8 @@ __global__ void __launch_bounds__(WQ_WARPS * 32)
 knn_wq_kernel(Geom gs, int m, int mpad, int nsample, int self, int qpw, const float4 *__restrict__ sp,
               const float4 *__restrict__ tlo, const float4 *__restrict__ thi, const float4 *__restrict__ glo,
               const float4 *__restrict__ ghi, const float4 *__restrict__ sq, const int *__restrict__ cell_start,
-              const uint32_t *__restrict__ bb, int *__restrict__ idx, float *__restrict__ dist2) {
+              const uint32_t *__restrict__ bb, int *__restrict__ idx, float *__restrict__ dist2,
+              int *__restrict__ order_out) {
     const int lane = threadIdx.x & 31;
     const int wq0 = (blockIdx.x * WQ_WARPS + (threadIdx.x >> 5)) * qpw;
     const int n = gs.n;
@@ -383,6 +384,8 @@ knn_wq_kernel(Geom gs, int m, int mpad, int nsample, int self, int qpw, const fl
         const int b = q / mpad;
         if (q - b * mpad >= m) continue;                      // padding slot of the query layout
         const float4 me = __ldg(sq + q);
+        // the visiting order (spatially coherent) for callers that want to process the queries the same way
+        if (order_out != nullptr && lane == 0) order_out[(long long)b * m + (q - b * mpad)] = __float_as_int(me.w);
         const float qx = me.x, qy = me.y, qz = me.z;
         WarpList<E> best;
         best.init(nsample, lane);
@@ -771,14 +774,14 @@ static void search_grid(const Built &B, int m, int &qpw, int &blocks) {
 // exact kNN with culling over nb clouds of n support / m query points; returns 0 or a cudaError_t.
 // idx (nb,m,nsample) holds indices local to the cloud, dist2 the squared distances.
 int knn_grid_batched(int nb, int n, int m, int nsample, const float *xyz, const float *new_xyz, int *idx,
-                     float *dist2, cudaStream_t st) {
+                     float *dist2, cudaStream_t st, int *order_out) {
     Scratch ws(st);
     Built B;
     cudaError_t e = build(ws, nb, n, m, xyz, new_xyz, B);
     if (e != cudaSuccess) return (int)e;
     int qpw, blocks;
     search_grid(B, m, qpw, blocks);
-#define KNN_WQ_ARGS B.gs, m, B.mpad, nsample, B.self, qpw, B.sp, B.tlo, B.thi, B.glo, B.ghi, B.sq, B.cell_start, B.bb, idx, dist2
+#define KNN_WQ_ARGS B.gs, m, B.mpad, nsample, B.self, qpw, B.sp, B.tlo, B.thi, B.glo, B.ghi, B.sq, B.cell_start, B.bb, idx, dist2, order_out
     if (nsample <= 32) knn_wq_kernel<1><<<blocks, WQ_WARPS * 32, 0, st>>>(KNN_WQ_ARGS);
     else if (nsample <= 64) knn_wq_kernel<2><<<blocks, WQ_WARPS * 32, 0, st>>>(KNN_WQ_ARGS);
     else knn_wq_kernel<4><<<blocks, WQ_WARPS * 32, 0, st>>>(KNN_WQ_ARGS);
@@ -786,8 +789,8 @@ int knn_grid_batched(int nb, int n, int m, int nsample, const float *xyz, const 
 }
 
 int knn_grid_single_segment(int n, int m, int nsample, const float *xyz, const float *new_xyz, int *idx,
-                            float *dist2, cudaStream_t st) {
-    return knn_grid_batched(1, n, m, nsample, xyz, new_xyz, idx, dist2, st);
+                            float *dist2, cudaStream_t st, int *order_out) {
+    return knn_grid_batched(1, n, m, nsample, xyz, new_xyz, idx, dist2, st, order_out);
 }
 
 // ball query with culling over nb clouds; idx (nb,m,nsample) pre-zeroed by the caller

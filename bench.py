@@ -175,7 +175,7 @@ def run_reference(args):
 def algorithmic_work(name, a):
     """(kind, amount) of algorithmic work of one C-ABI call from its leading int arguments.
     kind 'flop' -> FP32 FLOP (8 per pair: 3 sub, 3 mul, 2 add — BASELINE.md §4); 'byte' -> HBM bytes."""
-    if name == "amc3d_knnquery":
+    if name in ("amc3d_knnquery", "amc3d_knnquery_order"):
         n, m = a[0], a[1]
         return "flop", 8.0 * n * m
     if name in ("amc3d_ball_query", "amc3d_three_nn"):

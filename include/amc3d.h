@@ -130,6 +130,13 @@ int amc3d_three_interpolate_grad_ws(int b, int c, int n, int m, const float *gra
 int amc3d_knnquery(int n, int m, int nseg, int nsample, const float *xyz, const float *new_xyz,
                    const int *offset, const int *new_offset, int *idx, float *dist2,
                    void *stream);
+/* Same, additionally writing `order` (m) i32 (NULL = not wanted): a permutation of the queries in
+ * which consecutive entries are spatially close (the order the culled search visits them in;
+ * identity for the brute-force paths).  Feeding it to amc3d_amloss_forward_order makes the
+ * neighbour-row gathers of nearby anchors hit L1. */
+int amc3d_knnquery_order(int n, int m, int nseg, int nsample, const float *xyz, const float *new_xyz,
+                         const int *offset, const int *new_offset, int *idx, float *dist2,
+                         int *order, void *stream);
 
 /* out[i,s,:] = in[idx[i,s],:].  in (n,c), idx (m,nsample), out (m,nsample,c).
  * ref: pointops/src/grouping/grouping_cuda.cpp grouping_forward_cuda */
@@ -197,6 +204,13 @@ int amc3d_amloss_forward(int m, int d, int ke, int ld, const float *f, const flo
                          const int *nbr, const uint32_t *posbits, const float *a,
                          const amc3d_loss_params *params, float *loss_pt, float *ghat,
                          void *stream);
+
+/* Same, visiting the anchors in the order given (order (m) i32, a permutation of 0..m-1; NULL =
+ * index order).  Results are identical up to the summation order of the atomics. */
+int amc3d_amloss_forward_order(int m, int d, int ke, int ld, const float *f, const float *inv,
+                               const int *nbr, const uint32_t *posbits, const float *a,
+                               const amc3d_loss_params *params, float *loss_pt, float *ghat,
+                               const int *order, void *stream);
 
 /* loss_out[0] = sum_i loss_pt[i] / stats[0]  (deterministic, double accumulation; the
  * torch.mean over the selected points, MarginContrast.py:257; 0 selected -> NaN) */

@@ -85,6 +85,8 @@ def test_full_size_grouping_roundtrip_linearity():
     assert torch.equal(out.detach(), ref)
     g = torch.randn_like(out)
     out.backward(g)
-    lhs = (out.detach().double() * g.double()).sum()
+    terms = out.detach().double() * g.double()
+    lhs = terms.sum()
     rhs = (f.detach().double() * f.grad.double()).sum()
-    assert abs(lhs - rhs) <= 1e-6 * abs(lhs)
+    # the sum of ~2e8 zero-mean terms cancels to O(sqrt(N)): compare on that scale (FP32 scatter-add rounding)
+    assert abs(lhs - rhs) <= 1e-5 * terms.pow(2).sum().sqrt()
