@@ -347,21 +347,21 @@ fps_cluster_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, floa
 
         // ---- B. exact FPS on the candidate set for as long as its maximum provably beats every other
         //         point: the first pick is the global arg-max; a further pick is valid while its value
-        //         is > U, because values only shrink.  This loop is one dependent chain per pick
-        //         (arg-max -> winner's xyz -> candidates' new values), so it touches the candidates only;
-        //         the picks are parked in shared memory and applied to this thread's points afterwards,
-        //         where PPT independent chains keep the FP32 pipe busy.
-        const int j0 = j;
-        int q = 0, qa = 0;                 // picks made / picks to apply in this round
-        while (true) {
-            // this lane's best entry (first one on equal values), then the warp's
-            uint32_t bv = cv[0];
-            int be = 0;
+        //         is > U, because values only shrink.  The loop is one dependent chain per pick (arg-max
+        //         -> winner's xyz -> candidates' new values -> next arg-max).  Applying a pick to this
+        //         thread's own points is independent of that chain, so it is software-pipelined: the
+        //         body applies the PREVIOUS pick, giving ptxas PPT independent FP32 chains to fill the
+        //         chain's shuffle / vote / redux latencies with.  "No previous pick" is (inf,inf,inf),
+        //         which leaves every running distance unchanged — no branch in the body.
+        float px = INFINITY, py = INFINITY, pz = INFINITY;
+        int q = 0;
+        uint32_t bv = cv[0];
+        int be = 0;
 #pragma unroll
-            for (int c = 1; c < CPL; ++c)
-                if (cv[c] > bv) { bv = cv[c]; be = c; }
-            const uint32_t val = __reduce_max_sync(0xffffffffu, bv);
-            if (q > 0 && !(val > U)) break;
+        for (int c = 1; c < CPL; ++c)
+            if (cv[c] > bv) { bv = cv[c]; be = c; }
+        uint32_t val = __reduce_max_sync(0xffffffffu, bv);
+        while (true) {
             int neq = 0;                   // entries of this lane equal to the maximum
 #pragma unroll
             for (int c = 0; c < CPL; ++c) neq += cv[c] == val ? 1 : 0;
@@ -387,27 +387,32 @@ fps_cluster_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, floa
             x1 = __shfl_sync(0xffffffffu, sx, gl);
             y1 = __shfl_sync(0xffffffffu, sy, gl);
             z1 = __shfl_sync(0xffffffffu, sz, gl);
-            if (lane == gl)
-                sts_v4(a_picks + q * 16, __float_as_uint(sx), __float_as_uint(sy), __float_as_uint(sz), (uint32_t)sk);
+            if (rank == 0 && warp == 0 && lane == gl) idxs[j] = sk;
+            // the previous pick, on this thread's points (independent of everything above and below)
+#pragma unroll
+            for (int s = 0; s < PPT; ++s) t[s] = fminf(dist2_ref(x[s] - px, y[s] - py, z[s] - pz), t[s]);
             ++q;
             ++j;
-            if (j >= mm) break;            // like the reference, the last pick is never applied to temp
-            qa = q;
-            if (q == (NC < 64 ? NC : 64)) break;   // pick buffer full: go on in the next round
+            // like the reference, the last pick of the call is never applied to temp
+            const bool last = j >= mm;
+            px = last ? INFINITY : x1;
+            py = last ? INFINITY : y1;
+            pz = last ? INFINITY : z1;
+            // candidates' new values and the next arg-max
 #pragma unroll
             for (int c = 0; c < CPL; ++c)
                 cv[c] = min(cv[c], __float_as_uint(dist2_ref(cx[c] - x1, cy[c] - y1, cz[c] - z1)));
-        }
-        __syncwarp();
-        if (rank == 0 && warp == 0 && lane < q) idxs[j0 + lane] = (int)lds_b32(a_picks + lane * 16 + 12);
-        if (NC > 32 && rank == 0 && warp == 0 && lane + 32 < q) idxs[j0 + 32 + lane] = (int)lds_b32(a_picks + (lane + 32) * 16 + 12);
-#pragma unroll 2
-        for (int qq = 0; qq < qa; ++qq) {
-            const uint4 pk = lds_v4(a_picks + qq * 16);
-            const float px = __uint_as_float(pk.x), py = __uint_as_float(pk.y), pz = __uint_as_float(pk.z);
+            bv = cv[0];
+            be = 0;
 #pragma unroll
-            for (int s = 0; s < PPT; ++s) t[s] = fminf(dist2_ref(x[s] - px, y[s] - py, z[s] - pz), t[s]);
+            for (int c = 1; c < CPL; ++c)
+                if (cv[c] > bv) { bv = cv[c]; be = c; }
+            val = __reduce_max_sync(0xffffffffu, bv);
+            if (last || !(val > U)) break;
         }
+        // the round's final pick
+#pragma unroll
+        for (int s = 0; s < PPT; ++s) t[s] = fminf(dist2_ref(x[s] - px, y[s] - py, z[s] - pz), t[s]);
         par ^= 1;
         if (par == 0) phase ^= 1;
     }
