@@ -135,6 +135,71 @@ def cpu_path_replay(xyz, labels, k=16, seed=0):
     return float(loss.item())
 
 
+def ref_gpu_path_replay(xyz_t, labels_t, k=16, seed=0):
+    """The same call sequence on the GPU with the REFERENCE's own CUDA kernels (oracle/_ref, compiled
+    unmodified from the reference for sm_100) and the reference loss restated in torch on CUDA tensors —
+    the "reference recompiled on the same B200" baseline of BASELINE.md §3.  xyz_t (B,N,3), labels_t (B,N)."""
+    from amcontrast3d_b200.replay import XL, aa_args
+    from oracle import loss_oracle as lo
+    from oracle import ref_kernels as rk
+    g = torch.Generator(device=xyz_t.device)
+    g.manual_seed(seed)
+    B, N, _ = xyz_t.shape
+    n, C = [N], [XL["width"]]
+    for l in range(1, 5):
+        n.append(n[-1] // XL["strides"][l])
+        C.append(C[-1] * 2)
+    F = [torch.randn((B, C[l], n[l]), device=xyz_t.device, generator=g) for l in range(5)]
+    p = [xyz_t]
+    grouped = []
+    for l in range(1, 5):
+        idx, _ = rk.fps(p[l - 1], n[l])
+        p.append(torch.gather(p[l - 1], 1, idx.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous())
+        r = XL["radius"] * 2 ** (l - 1)
+        bq = rk.ball_query(r, 32, p[l - 1], p[l])
+        rk.group_points(p[l - 1].transpose(1, 2).contiguous(), bq)
+        grouped.append((rk.group_points(F[l - 1], bq), bq, n[l - 1]))
+        for _ in range(XL["blocks"][l] - 1):
+            bq = rk.ball_query(2 * r, 32, p[l], p[l])
+            rk.group_points(p[l].transpose(1, 2).contiguous(), bq)
+            grouped.append((rk.group_points(F[l], bq), bq, n[l]))
+    ups = []
+    for l in range(4, 0, -1):
+        d2, i3 = rk.three_nn(p[l - 1], p[l])
+        recip = 1.0 / (torch.sqrt(d2) + 1e-8)
+        w = (recip / recip.sum(2, keepdim=True)).contiguous()
+        ups.append((rk.three_interpolate(F[l], i3, w), i3, w, n[l]))
+    f_list = [torch.randn((B * n[s], C[s]), device=xyz_t.device, generator=g).requires_grad_(True) for s in range(4)]
+    sl = lo.make_stage_list([pp.reshape(-1, 3).contiguous() for pp in p[:4]], f_list)
+    loss, _, _, _ = lo.contrast_head_forward(labels_t.reshape(-1), sl, 13, None, aa_args(k), knn=rk.knnquery)
+    loss.backward()
+    for out, bq, nn in grouped:
+        rk.group_points_grad(out, bq, nn)
+    for out, i3, w, m in ups:
+        rk.three_interpolate_grad(out, i3, w, m)
+    torch.cuda.synchronize()
+    return float(loss.item())
+
+
+def time_ref_gpu(replay, k=16):
+    from oracle import ref_kernels as rk
+    if not rk.available():
+        return None
+    try:
+        ref_gpu_path_replay(replay.d_xyz, replay.d_labels, k)          # warm-up (allocator, module load)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        loss = ref_gpu_path_replay(replay.d_xyz, replay.d_labels, k)
+        ms = 1e3 * (time.perf_counter() - t0)
+    except Exception as e:                                             # a baseline must never break the bench
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    pts = replay.d_xyz.shape[0] * replay.d_xyz.shape[1]
+    return {"value": pts / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": 1, "loss": loss,
+            "kind": "the reference's own CUDA kernels (oracle/_ref: unmodified sources compiled for sm_100) for FPS / "
+                    "ball_query / grouping / three_nn / interpolate / knnquery + the reference loss restated in torch, "
+                    "same unit (8 x 24000 points) on the same GPU; host-timed, the reference launchers synchronise"}
+
+
 def time_cpu_sample(steps, warmup, k=16):
     from amcontrast3d_b200 import scenes
     from oracle import ops_oracle as oo
@@ -290,6 +355,38 @@ def run_ours(args):
             tdist.barrier()
         return ms, last
 
+    def timed_e2e(n_steps, graph):
+        """End to end with the host in the loop the way a trainer runs it: every step copies its inputs from
+        pinned host memory (async, stream-ordered before the step) and copies its loss back to pinned host
+        memory; the host READS the loss of step i while step i+1 is already queued (one step of lag, as
+        asynchronous logging does), so the device never idles waiting for Python."""
+        host_loss = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        evs = [torch.cuda.Event() for _ in range(2)]
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for i in range(n_steps):
+            loss = one_step(True, graph)
+            host_loss[i & 1].copy_(loss.detach().reshape(1), non_blocking=True)
+            evs[i & 1].record()
+            if i > 0:
+                evs[(i - 1) & 1].synchronize()
+                last = float(host_loss[(i - 1) & 1][0])
+        evs[(n_steps - 1) & 1].synchronize()
+        last = float(host_loss[(n_steps - 1) & 1][0])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+            ms = t.item()
+            tdist.barrier()
+        return ms, last
+
     warm = max(args.warmup, 3)
     for _ in range(warm):
         one_step(False, False)
@@ -317,13 +414,14 @@ def run_ours(args):
         sampler.start()
     ms_total, _ = timed(args.steps, False, use_graph)
     one_step(True, use_graph)
-    ms_e2e, last_loss = timed(e2e_steps, True, use_graph)
+    ms_e2e, last_loss = timed_e2e(args.steps, use_graph)
+    ms_e2e_blocking, _ = timed(e2e_steps, True, use_graph)     # host blocks on loss.item() every step
     clocks = sampler.stop() if rank == 0 else None
 
     ms_step = ms_total / args.steps
     pts = args.batch * args.points
     value = world * pts / (ms_step / 1e3)
-    e2e_value = world * pts / (ms_e2e / e2e_steps / 1e3)
+    e2e_value = world * pts / (ms_e2e / args.steps / 1e3)
 
     if rank != 0:
         if world > 1:
@@ -375,6 +473,9 @@ def run_ours(args):
         fps_row["us_per_pick"] = round(1e3 * fps_row["ms"] / picks, 4)
         fps_row["picks"] = picks
 
+    ref_gpu = None
+    if world == 1 and not args.no_cpu and not args.no_ref_gpu:
+        ref_gpu = time_ref_gpu(replay, args.k)
     cpu_baseline = None
     if world == 1 and not args.no_cpu:
         v, ms_cpu, cores = time_cpu_sample(1, 0, args.k)
@@ -390,10 +491,14 @@ def run_ours(args):
                        "l2": "working set per step (6.45 GB of grouped tensors) exceeds the 126 MB L2; no flush needed",
                        "grad_allreduce_mb": args.grad_mb if world > 1 else 0, "loss": last_loss},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": replay.h2d_bytes, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e / e2e_steps},
+                    "ms_per_step": ms_e2e / args.steps, "steps": args.steps,
+                    "host_loop": "inputs copied from pinned host memory and the loss copied back every step; the host "
+                                 "reads step i's loss while step i+1 is queued (one step of lag)",
+                    "blocking_ms_per_step": ms_e2e_blocking / e2e_steps},
             "gpu_launches": int(launches), "mode": "cuda-graph replay of the whole step" if use_graph else "eager",
             "eager": eager, "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm,
-            "kernels": kernels, "kernel_ms_per_step": round(total_ms, 3), "cpu_baseline": cpu_baseline}
+            "kernels": kernels, "kernel_ms_per_step": round(total_ms, 3), "cpu_baseline": cpu_baseline,
+            "ref_gpu": ref_gpu}
     print(json.dumps(line), flush=True)
     if world > 1:
         tdist.destroy_process_group()
@@ -414,6 +519,7 @@ def main():
     ap.add_argument("--k", type=int, default=16)
     ap.add_argument("--grad-mb", type=float, default=166.3, help="flat gradient all-reduce per step (N>1): PointNeXt-XL FP32 grads")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-CUDA-kernels-on-this-GPU baseline")
     ap.add_argument("--no-graph", action="store_true", help="time the eager (per-call Python) step instead of the CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":
