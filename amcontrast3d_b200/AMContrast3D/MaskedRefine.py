@@ -7,6 +7,43 @@ from torch.functional import F
 from .. import _amloss
 
 
+class LazyRate:
+    """Percentage of refined points, computed from a device counter only when somebody looks at it
+    (float(), comparison, arithmetic, formatting) — so DualMasks itself never synchronises with the host
+    and can be captured in a CUDA graph."""
+
+    def __init__(self, count, numel):
+        self.count, self.numel = count, numel
+
+    def __float__(self):
+        return (int(self.count.item()) / self.numel) * 100
+
+    def __eq__(self, other):
+        return float(self) == float(other)
+
+    def __lt__(self, other):
+        return float(self) < float(other)
+
+    def __add__(self, other):
+        return float(self) + float(other)
+
+    __radd__ = __add__
+
+    def __mul__(self, other):
+        return float(self) * float(other)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, other):
+        return float(self) / float(other)
+
+    def __format__(self, spec):
+        return format(float(self), spec)
+
+    def __repr__(self):
+        return repr(float(self))
+
+
 class RefinementMethod():
 
     def __init__(self, stage_list, p, f, a, i, B, K, fusion, threshold_max, threshold, gamma):
@@ -47,7 +84,7 @@ class RefinementMethod():
         chunk replacement, gamma blend (MaskedRefine.py:49-86; bug-compatible chunk view,
         SURVEY.md App. A.6) -> (feature (B,D,n), update rate in %)."""
         xyz = self.position.reshape(-1, 3).contiguous().float()
-        o = torch.tensor([xyz.shape[0]], dtype=torch.int32, device=xyz.device)
+        o = torch.full((1,), xyz.shape[0], dtype=torch.int32, device=xyz.device)   # no host->device copy
         knn_idx, _ = _amloss.knn_raw(self.sample_k, xyz, xyz, o, o)
         self.sample_k -= 1                                     # the reference mutates it too (:59)
         f = self.feature.contiguous()
@@ -60,8 +97,9 @@ class RefinementMethod():
             count = torch.zeros((1,), dtype=torch.int32, device=f.device)
             self.feature = _amloss.DualMasksFunction.apply(f, a, jmin, self.threshold, self.threshold_max,
                                                            self.gamma, count)
-            rate = (count.item() / a.numel()) * 100
-            return self.feature, rate
+            # the reference returns a Python float here (a host synchronisation per decoder stage); the
+            # value is only logged, so it is handed back lazily: float(rate) / formatting reads it
+            return self.feature, LazyRate(count, a.numel())
         elif self.fusion == 'MIN_ALL0':
             D = f.shape[1]
             nidx = knn_idx[:, 1:].reshape(-1).long()

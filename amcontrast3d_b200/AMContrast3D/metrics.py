@@ -8,7 +8,7 @@ from .. import _amloss
 def posmask_searching(xyz, target, nsample, num_classes, ignore_index):
     """xyz (n,3), target (n) i64 -> (posmask (n,nsample-1) bool, neighbor_idx (n,nsample-1) i32)"""
     xyz = xyz.contiguous().float()
-    o = torch.tensor([xyz.shape[0]], dtype=torch.int32, device=xyz.device)
+    o = torch.full((1,), xyz.shape[0], dtype=torch.int32, device=xyz.device)
     cls, _ = _amloss.stage_labels(target, num_classes, ignore_index, None)
     knn_idx, _ = _amloss.knn_raw(nsample, xyz, xyz, o, o)
     nl = _amloss.NeighbourList(knn_idx, drop_self=True)

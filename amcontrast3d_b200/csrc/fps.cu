@@ -171,7 +171,11 @@ __device__ __forceinline__ float tree_max(const float (&t)[N]) {
 //     bit mask of independent compares (no serial compare/select chain over the PPT slots);
 //   * tie keys are evaluated only when two maxima are bit-equal (never, on real scenes);
 //   * shared-memory addresses are plain 32-bit registers computed before the loop.
-template <int CS, int PPT, int NW>
+// SX = false: every thread keeps its points' coordinates in registers (the fast layout).  SX = true: they
+// stay in shared memory as three planes (12 bytes per point, up to ~13 000 points per CTA) and only the
+// running distances live in registers — for scenes of 100k - 210k points, which no longer fit the register
+// file of a 16-CTA cluster.
+template <int CS, int PPT, int NW, bool SX>
 __global__ void __launch_bounds__(NW * 32)
 fps_cluster_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, float *__restrict__ temp,
                    int *__restrict__ idxs, int dbg) {
@@ -180,10 +184,11 @@ fps_cluster_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, floa
     constexpr int CPL = (NC + 31) / 32;      // candidates per lane
     static_assert(NC <= 256, "too many candidates");
     extern __shared__ float4 s_pts[];                              // [PPT][NT] copy of this CTA's points
+    float *s_soa = reinterpret_cast<float *>(s_pts);               // SX: planes x | y | z, each [PPT][NT]
+    constexpr int PL = PPT * NT;                                   // plane length
     __shared__ __align__(16) unsigned char s_warp[2][NW][CAND_BYTES];   // per-warp candidates
     __shared__ __align__(16) unsigned char s_exch[2][NC][CAND_BYTES];   // every warp's candidate, whole cluster
     __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ __align__(16) unsigned char s_picks[NW][(NC < 64 ? NC : 64) * 16];   // this round's picks, one copy per warp
 
     const int tid = (int)pin(threadIdx.x), lane = tid & 31, warp = tid >> 5;
     const int rank = (int)cluster_ctarank();
@@ -200,24 +205,30 @@ fps_cluster_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, floa
     const int kbase = rank + CS * (warp + NW * lane);     // index of slot 0
     constexpr int KSTRIDE = CS * NW * 32;                 // index distance between slots
 
-    float x[PPT], y[PPT], z[PPT], t[PPT];
+    float x[SX ? 1 : PPT], y[SX ? 1 : PPT], z[SX ? 1 : PPT], t[PPT];
     bool any_valid = false;
 #pragma unroll
     for (int s = 0; s < PPT; ++s) {
         const int k = kbase + s * KSTRIDE;
+        // +inf coordinates give d = +inf and fminf(inf, 0) = 0: a padding slot stays at
+        // distance 0 and is excluded from tie resolution below
+        float px0 = INFINITY, py0 = INFINITY, pz0 = INFINITY;
+        t[s] = 0.f;
         if (k < n) {
-            x[s] = __ldg(xyz + 3ll * k);
-            y[s] = __ldg(xyz + 3ll * k + 1);
-            z[s] = __ldg(xyz + 3ll * k + 2);
+            px0 = __ldg(xyz + 3ll * k);
+            py0 = __ldg(xyz + 3ll * k + 1);
+            pz0 = __ldg(xyz + 3ll * k + 2);
             t[s] = temp[k];
             any_valid = true;
-        } else {
-            // +inf coordinates give d = +inf and fminf(inf, 0) = 0: a padding slot stays at
-            // distance 0 and is excluded from tie resolution below
-            x[s] = y[s] = z[s] = INFINITY;
-            t[s] = 0.f;
         }
-        s_pts[s * NT + tid] = make_float4(x[s], y[s], z[s], 0.f);
+        if (SX) {
+            s_soa[s * NT + tid] = px0;
+            s_soa[PL + s * NT + tid] = py0;
+            s_soa[2 * PL + s * NT + tid] = pz0;
+        } else {
+            x[s] = px0; y[s] = py0; z[s] = pz0;
+            s_pts[s * NT + tid] = make_float4(px0, py0, pz0, 0.f);
+        }
     }
     const bool warp_valid = __any_sync(0xffffffffu, any_valid);
 
@@ -245,7 +256,6 @@ fps_cluster_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, floa
     const uint32_t a_warp0 = pin(smem_u32(&s_warp[0][0][0]));      // + par*NW*32 + w*32
     const uint32_t a_exch0 = pin(smem_u32(&s_exch[0][0][0]));      // + par*CS*32 + r*32
     const uint32_t lbar0 = pin(smem_u32(&s_bar[0])), lbar1 = pin(smem_u32(&s_bar[1]));
-    const uint32_t a_picks = pin(smem_u32(&s_picks[warp][0]));
     const int mm = (int)pin((uint32_t)m);
     // warp 0, lane r delivers this CTA's candidate to CTA r of the cluster
     const uint32_t peer = lane < CS ? lane : 0;
@@ -253,12 +263,21 @@ fps_cluster_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, floa
     const uint32_t dst1 = mapa_u32(a_exch0 + (NC + rank * NW) * CAND_BYTES, peer);
     const uint32_t rbar0 = mapa_u32(lbar0, peer), rbar1 = mapa_u32(lbar1, peer);
 
+    // running-distance update of this thread's points with one pick
+    auto apply_pick = [&](float qx, float qy, float qz) {
+#pragma unroll
+        for (int s = 0; s < PPT; ++s) {
+            if (SX) {
+                const float ax = s_soa[s * NT + tid], ay = s_soa[PL + s * NT + tid], az = s_soa[2 * PL + s * NT + tid];
+                t[s] = fminf(dist2_ref(ax - qx, ay - qy, az - qz), t[s]);
+            } else {
+                t[s] = fminf(dist2_ref(x[s] - qx, y[s] - qy, z[s] - qz), t[s]);
+            }
+        }
+    };
     // the first pick (index 0) is applied before the loop, so that t[] is always up to date
     // with every pick made so far when a round starts
-    if (m > 1) {
-#pragma unroll
-        for (int s = 0; s < PPT; ++s) t[s] = fminf(dist2_ref(x[s] - x1, y[s] - y1, z[s] - z1), t[s]);
-    }
+    if (m > 1) apply_pick(x1, y1, z1);
 
     uint32_t par = 0, phase = 0;
     int j = 1, rounds = 0;
@@ -298,7 +317,14 @@ fps_cluster_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, floa
             const uint32_t sec = __reduce_max_sync(0xffffffffu, __float_as_uint(lane == src ? v2 : v1));
             if (lane == src) {
                 if (bslot >= 0) {
-                    const uint4 cp = lds_v4(a_pts + bslot * (NT * 16));
+                    uint4 cp;
+                    if (SX) {
+                        cp.x = __float_as_uint(s_soa[bslot * NT + tid]);
+                        cp.y = __float_as_uint(s_soa[PL + bslot * NT + tid]);
+                        cp.z = __float_as_uint(s_soa[2 * PL + bslot * NT + tid]);
+                    } else {
+                        cp = lds_v4(a_pts + bslot * (NT * 16));
+                    }
                     sts_v4(my_warp_slot, wv, (uint32_t)(kbase + bslot * KSTRIDE), cp.x, cp.y);
                     sts_v2(my_warp_slot + 16, cp.z, sec);
                 } else {
@@ -389,8 +415,7 @@ fps_cluster_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, floa
             z1 = __shfl_sync(0xffffffffu, sz, gl);
             if (rank == 0 && warp == 0 && lane == gl) idxs[j] = sk;
             // the previous pick, on this thread's points (independent of everything above and below)
-#pragma unroll
-            for (int s = 0; s < PPT; ++s) t[s] = fminf(dist2_ref(x[s] - px, y[s] - py, z[s] - pz), t[s]);
+            apply_pick(px, py, pz);
             ++q;
             ++j;
             // like the reference, the last pick of the call is never applied to temp
@@ -411,8 +436,7 @@ fps_cluster_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, floa
             if (last || !(val > U)) break;
         }
         // the round's final pick
-#pragma unroll
-        for (int s = 0; s < PPT; ++s) t[s] = fminf(dist2_ref(x[s] - px, y[s] - py, z[s] - pz), t[s]);
+        apply_pick(px, py, pz);
         par ^= 1;
         if (par == 0) phase ^= 1;
     }
@@ -470,11 +494,11 @@ fps_global_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, float
     }
 }
 
-template <int CS, int PPT, int NW>
+template <int CS, int PPT, int NW, bool SX = false>
 static cudaError_t launch_cluster(int b, int n, int m, int log2bs, const float *xyz, float *temp, int *idx,
                                   cudaStream_t st) {
-    const size_t smem = sizeof(float4) * PPT * NW * 32;
-    auto kern = fps_cluster_kernel<CS, PPT, NW>;
+    const size_t smem = (SX ? 3 * sizeof(float) : sizeof(float4)) * PPT * NW * 32;
+    auto kern = fps_cluster_kernel<CS, PPT, NW, SX>;
     cudaError_t e;
     if (smem > 40 * 1024) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -515,6 +539,10 @@ static cudaError_t launch_for_ppt(int ppt, int b, int n, int m, int log2bs, cons
     if (NW <= 8) {     // 24+ points per thread only fit the register file with <= 256 threads
         if (ppt <= 24) return launch_cluster<CS, 24, (NW <= 8 ? NW : 8)>(FPS_ARGS);
         if (NW <= 4 && ppt <= 32) return launch_cluster<CS, 32, (NW <= 4 ? NW : 4)>(FPS_ARGS);
+    }
+    if (NW == 16 && CS == 16) {   // coordinates in shared memory: up to 16 x 512 x 26 = 212 992 points per scene
+        if (ppt <= 20) return launch_cluster<16, 20, 16, true>(FPS_ARGS);
+        if (ppt <= 26) return launch_cluster<16, 26, 16, true>(FPS_ARGS);
     }
     return cudaErrorInvalidConfiguration;
 }

@@ -132,7 +132,7 @@ def test_fps_matches_reference_sequence(n, m, b):
     assert np.array_equal(idx.cpu().numpy(), ridx)
 
 
-@pytest.mark.parametrize("n,m", [(64000, 300), (70000, 64)])
+@pytest.mark.parametrize("n,m", [(64000, 300), (70000, 64), (100000, 200), (150000, 300), (200000, 200), (230000, 40)])
 def test_fps_large_scenes(n, m):
     """ScanNet-sized scenes: 16-CTA cluster path and the global-memory fallback"""
     from amcontrast3d_b200.layers import furthest_point_sample
