@@ -20,7 +20,8 @@ from .AEF.ambiguity import ambiguity_function
 
 def _stage_ambiguity(n, i, stageACE_list, target, num_classes, ignore_index, ambiguity_args, nstride, ftype):
     """Steps 1-4 of SURVEY.md App. A.4 for one stage -> dict(p, features, nl, posbits, cnt, a, stats, knn_idx)."""
-    p, features, o = fetch_pxo(n, i, stageACE_list, ftype)
+    stage = stageACE_list[n][i]
+    p, features, o = stage['p_out'], stage.get('f_out'), stage['offset']     # fetch_pxo; features may be absent
     p = p.contiguous()
     if p.dtype != torch.float32:
         p = p.float()
@@ -120,10 +121,24 @@ class ContrastHead(nn.Module):
             raise ValueError(f'unknown supervisedCL {ambiguity_args.supervisedCL!r}')
         return -torch.log(loss)
 
+    def precompute_geometry(self, i, stageACE_list, target, num_classes, ignore_index, ambiguity_args):
+        """Everything of stage i that depends on coordinates and labels only — stage labels, kNN, posmask,
+        ambiguity (steps 1-4 of SURVEY.md App. A.4) — so that a trainer can run it ahead of time, e.g. on a
+        side stream next to the encoder.  `stageACE_list[stages][s]` needs 'p_out' and 'offset' for s = 0
+        and s = i only.  Put the returned objects in stageACE_list['am_geometry'] (a list indexed by stage,
+        None = compute as usual) and forward() uses them; results are identical."""
+        return _stage_ambiguity(ambiguity_args.stages, i, stageACE_list, target, num_classes, ignore_index,
+                                ambiguity_args, self.nstride, self.ftype)
+
     def point_contrast_margin(self, n, i, stageACE_list, target, num_classes, ignore_index, ambiguity_args):
         """One stage (MarginContrast.py:220-259) -> (loss, output_ai, target_ai)."""
-        st = _stage_ambiguity(n, i, stageACE_list, target, num_classes, ignore_index, ambiguity_args,
-                              self.nstride, self.ftype)
+        pre = stageACE_list.get('am_geometry') if hasattr(stageACE_list, 'get') else None
+        if pre is not None and pre[i] is not None:
+            st = dict(pre[i])
+            st['features'] = stageACE_list[n][i]['f_out']
+        else:
+            st = _stage_ambiguity(n, i, stageACE_list, target, num_classes, ignore_index, ambiguity_args,
+                                  self.nstride, self.ftype)
         a = st['a']
         target_ai = torch.clone(a)
         output_ai = stageACE_list['ambiguity'][i].flatten() if 'ambiguity' in stageACE_list.keys() else None

@@ -94,8 +94,12 @@ class QueryAndGroup(nn.Module):
         self.relative_xyz = relative_xyz
         self.return_only_idx = return_only_idx
 
-    def forward(self, query_xyz, support_xyz, features=None):
-        idx = ball_query(self.radius, self.nsample, support_xyz, query_xyz)
+    def forward(self, query_xyz, support_xyz, features=None, idx=None):
+        """`idx` (not in the reference signature, optional): the result of
+        ball_query(self.radius, self.nsample, support_xyz, query_xyz) when the caller has already computed
+        it, e.g. on a geometry stream running ahead of the feature path (replay.py)."""
+        if idx is None:
+            idx = ball_query(self.radius, self.nsample, support_xyz, query_xyz)
         if self.return_only_idx:
             return idx
         grouped_xyz = grouping_operation(support_xyz.transpose(1, 2).contiguous(), idx)

@@ -66,10 +66,11 @@ class ThreeInterpolate(Function):
 three_interpolate = ThreeInterpolate.apply
 
 
-def three_interpolation(unknown_xyz, known_xyz, know_feat):
+def three_interpolation(unknown_xyz, known_xyz, know_feat, nn=None):
     """Inverse-distance interpolation from the 3 nearest known points (ref: upsampling.py:92-102).
-    unknown_xyz (B,n,3), known_xyz (B,m,3), know_feat (B,C,m) -> (B,C,n)."""
-    dist, idx = three_nn(unknown_xyz, known_xyz)
+    unknown_xyz (B,n,3), known_xyz (B,m,3), know_feat (B,C,m) -> (B,C,n).
+    `nn` (not in the reference signature, optional): a precomputed three_nn(unknown_xyz, known_xyz)."""
+    dist, idx = three_nn(unknown_xyz, known_xyz) if nn is None else nn
     dist_recip = 1.0 / (dist + 1e-8)
     norm = torch.sum(dist_recip, dim=2, keepdim=True)
     weight = dist_recip / norm

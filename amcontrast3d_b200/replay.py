@@ -44,13 +44,21 @@ class PathReplay:
 
     def __init__(self, batch=8, n_points=24000, device="cuda", k=16, num_classes=13, ignore_index=None,
                  kind="surface", rank=0, first_scene=0, arch=XL, refine=False, refine_k=12, seed=0,
-                 with_grouping=True, with_loss=True):
+                 with_grouping=True, with_loss=True, geometry_stream=True):
         self.B, self.N, self.device = batch, n_points, torch.device(device)
         self.num_classes, self.ignore_index = num_classes, ignore_index
         self.args = aa_args(k)
         self.arch = arch
         self.refine, self.refine_k = refine, refine_k
         self.with_grouping, self.with_loss = with_grouping, with_loss
+        # FPS, ball_query and three_nn depend on coordinates only.  With geometry_stream they run on a side
+        # stream that works ahead of the feature path (in a real step: ahead of the MLPs as well): the
+        # latency-bound FPS clusters and the search kernels overlap the HBM-bound grouping kernels.  Same
+        # operator calls, same results; only the issue order and the stream differ.
+        self.geometry_stream = geometry_stream and torch.cuda.is_available()
+        self._geo = None
+        self._geo2 = None
+        self._am_geometry = None
         xyz, labels = scenes.batch_of_scenes(batch, n_points, kind, rank=rank, first_scene=first_scene,
                                              num_classes=num_classes,
                                              ignore_fraction=0.05 if ignore_index is not None else 0.0)
@@ -101,17 +109,80 @@ class PathReplay:
         arch = self.arch
         p = [p0]
         outs = []
-        for l in range(1, len(arch["blocks"])):
-            idx = furthest_point_sample(p[l - 1], self.n[l]).long()
-            p.append(torch.gather(p[l - 1], 1, idx.unsqueeze(-1).expand(-1, -1, 3)).contiguous())
-            if self.with_grouping:
-                dp, fj = self.sa[l](p[l], p[l - 1], self.F[l - 1])
-                outs.append(fj)
-                for _ in range(arch["blocks"][l] - 1):
-                    dp, fj = self.la[l](p[l], p[l], self.F[l])
+        nlev = len(arch["blocks"])
+        if self.geometry_stream:
+            from .layers import ball_query, three_nn
+            main = torch.cuda.current_stream(self.device)
+            if self._geo is None:
+                self._geo = torch.cuda.Stream(device=self.device)
+            geo = self._geo
+            geo.wait_stream(main)                                   # fork (inputs are ready on `main`)
+            ev_lvl, ev_up, bq_sa, bq_la, nn3 = [None], [None] * nlev, [None], [None], [None] * nlev
+            ev_pts = [None] * nlev
+            with torch.cuda.stream(geo):
+                for l in range(1, nlev):
+                    idx = furthest_point_sample(p[l - 1], self.n[l]).long()
+                    p.append(torch.gather(p[l - 1], 1, idx.unsqueeze(-1).expand(-1, -1, 3)).contiguous())
+                    ev_pts[l] = torch.cuda.Event()
+                    ev_pts[l].record(geo)
+                    sa_idx, la_idx = None, []
+                    if self.with_grouping:
+                        sa_idx = ball_query(self.sa[l].radius, self.sa[l].nsample, p[l - 1], p[l])
+                        la_idx = [ball_query(self.la[l].radius, self.la[l].nsample, p[l], p[l])
+                                  for _ in range(arch["blocks"][l] - 1)]
+                    bq_sa.append(sa_idx)
+                    bq_la.append(la_idx)
+                    ev = torch.cuda.Event()
+                    ev.record(geo)
+                    ev_lvl.append(ev)
+                for l in range(nlev - 1, 0, -1):
+                    nn3[l] = three_nn(p[l - 1], p[l])
+                    ev_up[l] = torch.cuda.Event()
+                    ev_up[l].record(geo)
+            # the loss's own geometry (stage labels, kNN, posmask, ambiguity: coordinates + labels only) on a
+            # second side stream: stage 0 needs nothing but the input cloud, so its 192 000-point kNN runs
+            # while the first FPS — a latency-bound chain that leaves most of the GPU idle — is in flight
+            if self.with_loss:
+                if self._geo2 is None:
+                    self._geo2 = torch.cuda.Stream(device=self.device)
+                geo2 = self._geo2
+                geo2.wait_stream(main)
+                with torch.cuda.stream(geo2):
+                    pts, self._am_geometry = [], []
+                    for s in range(4):
+                        if s > 0:
+                            geo2.wait_event(ev_pts[s])
+                        pts.append({"p_out": p[s].reshape(-1, 3), "offset": self._offsets[s]})
+                        sl = {"down": pts, "up": pts}
+                        self._am_geometry.append(self.head.precompute_geometry(
+                            s, sl, labels.reshape(-1), self.num_classes, self.ignore_index, self.args))
+            for l in range(1, nlev):
+                main.wait_event(ev_lvl[l])
+                if self.with_grouping:
+                    dp, fj = self.sa[l](p[l], p[l - 1], self.F[l - 1], idx=bq_sa[l])
                     outs.append(fj)
-        for l in range(len(arch["blocks"]) - 1, 0, -1):
-            outs.append(three_interpolation(p[l - 1], p[l], self.F[l]))
+                    for i in range(arch["blocks"][l] - 1):
+                        dp, fj = self.la[l](p[l], p[l], self.F[l], idx=bq_la[l][i])
+                        outs.append(fj)
+            for l in range(nlev - 1, 0, -1):
+                main.wait_event(ev_up[l])
+                outs.append(three_interpolation(p[l - 1], p[l], self.F[l], nn=nn3[l]))
+            main.wait_stream(geo)                                   # join
+            if self.with_loss:
+                main.wait_stream(self._geo2)
+        else:
+            self._am_geometry = None
+            for l in range(1, nlev):
+                idx = furthest_point_sample(p[l - 1], self.n[l]).long()
+                p.append(torch.gather(p[l - 1], 1, idx.unsqueeze(-1).expand(-1, -1, 3)).contiguous())
+                if self.with_grouping:
+                    dp, fj = self.sa[l](p[l], p[l - 1], self.F[l - 1])
+                    outs.append(fj)
+                    for _ in range(arch["blocks"][l] - 1):
+                        dp, fj = self.la[l](p[l], p[l], self.F[l])
+                        outs.append(fj)
+            for l in range(nlev - 1, 0, -1):
+                outs.append(three_interpolation(p[l - 1], p[l], self.F[l]))
         loss = None
         if self.with_loss:
             feats = self.f_dec
@@ -126,6 +197,8 @@ class PathReplay:
             down = [{"p_out": p[s].reshape(-1, 3), "f_out": feats[s],
                      "offset": self._offsets[s]} for s in range(4)]
             stage_list = {"inputs": None, "down": down, "up": down}
+            if self._am_geometry is not None:
+                stage_list["am_geometry"] = self._am_geometry
             loss, a_cat, _ = self.head(None, labels.reshape(-1), stage_list, self.num_classes, self.ignore_index,
                                        self.args)
         return loss, outs
