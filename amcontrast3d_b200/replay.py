@@ -44,7 +44,7 @@ class PathReplay:
 
     def __init__(self, batch=8, n_points=24000, device="cuda", k=16, num_classes=13, ignore_index=None,
                  kind="surface", rank=0, first_scene=0, arch=XL, refine=False, refine_k=12, seed=0,
-                 with_grouping=True, with_loss=True, geometry_stream=True):
+                 with_grouping=True, with_loss=True, geometry_stream=True, prefetch=False):
         self.B, self.N, self.device = batch, n_points, torch.device(device)
         self.num_classes, self.ignore_index = num_classes, ignore_index
         self.args = aa_args(k)
@@ -59,6 +59,14 @@ class PathReplay:
         self._geo = None
         self._geo2 = None
         self._am_geometry = None
+        # prefetch: a software pipeline across steps.  The FPS chain of a batch (and the first ball query,
+        # which everything at level 1 waits for) depends on its coordinates only, so it is computed one step
+        # EARLY, on a side stream, while the previous batch's feature path and backward keep HBM busy — the
+        # way a data loader prefetches.  Every step still runs one full FPS chain and one full feature pass;
+        # the ~1.7 ms of start-up latency at the head of the step disappears from the critical path.
+        self.prefetch = prefetch and self.geometry_stream
+        self._geoN = None
+        self._pf = None           # {'p': [p1..p4] static, 'sa1': static idx, 'next': (tmp p list, tmp sa1)}
         xyz, labels = scenes.batch_of_scenes(batch, n_points, kind, rank=rank, first_scene=first_scene,
                                              num_classes=num_classes,
                                              ignore_fraction=0.05 if ignore_index is not None else 0.0)
@@ -104,6 +112,8 @@ class PathReplay:
 
     def forward(self, xyz=None, labels=None):
         """-> (loss, outputs needing a synthetic upstream gradient)"""
+        if self.prefetch:
+            return self._forward_prefetch(xyz, labels)
         p0 = self.d_xyz if xyz is None else xyz
         labels = self.d_labels if labels is None else labels
         arch = self.arch
@@ -183,6 +193,9 @@ class PathReplay:
                         outs.append(fj)
             for l in range(nlev - 1, 0, -1):
                 outs.append(three_interpolation(p[l - 1], p[l], self.F[l]))
+        return self._loss_tail(p, labels), outs
+
+    def _loss_tail(self, p, labels):
         loss = None
         if self.with_loss:
             feats = self.f_dec
@@ -201,7 +214,104 @@ class PathReplay:
                 stage_list["am_geometry"] = self._am_geometry
             loss, a_cat, _ = self.head(None, labels.reshape(-1), stage_list, self.num_classes, self.ignore_index,
                                        self.args)
-        return loss, outs
+        return loss
+
+    # ------------------------------------------------------------------------------------
+    def _fps_chain(self, p0):
+        q = [p0]
+        for l in range(1, len(self.arch["blocks"])):
+            idx = furthest_point_sample(q[l - 1], self.n[l]).long()
+            q.append(torch.gather(q[l - 1], 1, idx.unsqueeze(-1).expand(-1, -1, 3)).contiguous())
+        return q
+
+    def _forward_prefetch(self, xyz=None, labels=None):
+        """Pipelined schedule: `xyz` / `labels` (if given) are the NEXT batch; the batch whose FPS chain was
+        prefetched during the previous call goes through the feature path now."""
+        from .layers import ball_query, three_nn
+        arch, nlev = self.arch, len(self.arch["blocks"])
+        main = torch.cuda.current_stream(self.device)
+        if self._pf is None:
+            # prologue (eager, once): buffers for the next batch and the current batch's FPS chain
+            self.d_xyz_next, self.d_labels_next = self.d_xyz.clone(), self.d_labels.clone()
+            q = self._fps_chain(self.d_xyz)
+            sa1 = ball_query(self.sa[1].radius, self.sa[1].nsample, q[0], q[1]) if self.with_grouping else None
+            self._pf = {"p": q[1:], "sa1": sa1, "next": None}
+            for name in ("_geo", "_geo2", "_geoN"):
+                setattr(self, name, torch.cuda.Stream(device=self.device))
+        if xyz is not None:
+            self.d_xyz_next.copy_(xyz, non_blocking=True)
+        if labels is not None:
+            self.d_labels_next.copy_(labels, non_blocking=True)
+        geo, geo2, geoN = self._geo, self._geo2, self._geoN
+        for st in (geo, geo2, geoN):
+            st.wait_stream(main)                                    # fork
+        # next batch: FPS chain + the first ball query, nothing on the current step waits for this
+        with torch.cuda.stream(geoN):
+            q = self._fps_chain(self.d_xyz_next)
+            sa1n = ball_query(self.sa[1].radius, self.sa[1].nsample, q[0], q[1]) if self.with_grouping else None
+            self._pf["next"] = (q[1:], sa1n)
+        # current batch: its points exist already, so every search can start at once
+        p = [self.d_xyz] + self._pf["p"]
+        labels_cur = self.d_labels
+        outs = []
+        ev_lvl, ev_up, bq_sa, bq_la, nn3 = [None], [None] * nlev, [None], [None], [None] * nlev
+        with torch.cuda.stream(geo):
+            for l in range(1, nlev):
+                sa_idx, la_idx = None, []
+                if self.with_grouping:
+                    sa_idx = self._pf["sa1"] if l == 1 else ball_query(self.sa[l].radius, self.sa[l].nsample, p[l - 1], p[l])
+                    la_idx = [ball_query(self.la[l].radius, self.la[l].nsample, p[l], p[l])
+                              for _ in range(arch["blocks"][l] - 1)]
+                bq_sa.append(sa_idx)
+                bq_la.append(la_idx)
+                ev = torch.cuda.Event()
+                ev.record(geo)
+                ev_lvl.append(ev)
+            for l in range(nlev - 1, 0, -1):
+                nn3[l] = three_nn(p[l - 1], p[l])
+                ev_up[l] = torch.cuda.Event()
+                ev_up[l].record(geo)
+        if self.with_loss:
+            with torch.cuda.stream(geo2):
+                pts, self._am_geometry = [], []
+                for s in range(4):
+                    pts.append({"p_out": p[s].reshape(-1, 3), "offset": self._offsets[s]})
+                    sl = {"down": pts, "up": pts}
+                    self._am_geometry.append(self.head.precompute_geometry(
+                        s, sl, labels_cur.reshape(-1), self.num_classes, self.ignore_index, self.args))
+        for l in range(1, nlev):
+            if self.with_grouping:
+                # the level-1 SetAbstraction grouping needs no search of this step at all
+                dp, fj = self.sa[l](p[l], p[l - 1], self.F[l - 1], idx=bq_sa[l]) if l == 1 else (None, None)
+                if l == 1:
+                    outs.append(fj)
+            main.wait_event(ev_lvl[l])
+            if self.with_grouping:
+                if l > 1:
+                    dp, fj = self.sa[l](p[l], p[l - 1], self.F[l - 1], idx=bq_sa[l])
+                    outs.append(fj)
+                for i in range(arch["blocks"][l] - 1):
+                    dp, fj = self.la[l](p[l], p[l], self.F[l], idx=bq_la[l][i])
+                    outs.append(fj)
+        for l in range(nlev - 1, 0, -1):
+            main.wait_event(ev_up[l])
+            outs.append(three_interpolation(p[l - 1], p[l], self.F[l], nn=nn3[l]))
+        main.wait_stream(geo)                                       # join (geoN is joined after the backward)
+        main.wait_stream(geo2)
+        return self._loss_tail(p, labels_cur), outs
+
+    def _rotate_prefetch(self):
+        """End of a pipelined step: the prefetched chain becomes the current batch's."""
+        main = torch.cuda.current_stream(self.device)
+        main.wait_stream(self._geoN)
+        q, sa1n = self._pf["next"]
+        for dst, src in zip(self._pf["p"], q):
+            dst.copy_(src)
+        if sa1n is not None:
+            self._pf["sa1"].copy_(sa1n)
+        self.d_xyz.copy_(self.d_xyz_next)
+        self.d_labels.copy_(self.d_labels_next)
+        self._pf["next"] = None
 
     @property
     def _offsets(self):
@@ -227,6 +337,8 @@ class PathReplay:
             tensors.append(loss)
             grads.append(None)
         torch.autograd.backward(tensors, grads)
+        if self.prefetch:
+            self._rotate_prefetch()
         return loss
 
     def step_e2e(self):
@@ -273,8 +385,8 @@ class PathReplay:
         """Replay the captured step.  With host tensors given, they are first copied (async, from
         pinned memory) into the static device buffers the graph reads.  Returns the loss tensor."""
         if h_xyz is not None:
-            self.d_xyz.copy_(h_xyz, non_blocking=True)
+            (self.d_xyz_next if self.prefetch else self.d_xyz).copy_(h_xyz, non_blocking=True)
         if h_labels is not None:
-            self.d_labels.copy_(h_labels, non_blocking=True)
+            (self.d_labels_next if self.prefetch else self.d_labels).copy_(h_labels, non_blocking=True)
         self._graph.replay()
         return self._graph_loss

@@ -306,13 +306,17 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     _capi.load(build_if_missing=False)
 
-    replay = PathReplay(batch=args.batch, n_points=args.points, device=dev, k=args.k, rank=rank)
+    replay = PathReplay(batch=args.batch, n_points=args.points, device=dev, k=args.k, rank=rank,
+                        prefetch=not args.no_prefetch)
     stats_layout = amdist.PackedStats(13)
     buckets = amdist.GradBuckets(int(args.grad_mb * 1e6 / 4), dev) if world > 1 and args.grad_mb > 0 else None
 
     use_graph = not args.no_graph
 
+    cur = {"replay": replay}
+
     def one_step(e2e=False, graph=False):
+        replay = cur["replay"]
         nb = len(buckets.buckets) if buckets is not None else 0
         if world > 1 and buckets is not None and nb > 1:
             buckets.launch(0, nb - 1)            # ready during the backward in DDP: overlaps the step
@@ -418,6 +422,25 @@ def run_ours(args):
     ms_e2e_blocking, _ = timed(e2e_steps, True, use_graph)     # host blocks on loss.item() every step
     clocks = sampler.stop() if rank == 0 else None
 
+    # the same unit WITHOUT the cross-step pipeline (every step starts with its own FPS chain), for comparison
+    unpipelined = None
+    if replay.prefetch:
+        ru = PathReplay(batch=args.batch, n_points=args.points, device=dev, k=args.k, rank=rank, prefetch=False)
+        cur["replay"] = ru
+        for _ in range(warm):
+            one_step(False, False)
+        if use_graph:
+            ru.capture(warmup=1)
+            for _ in range(warm):
+                one_step(False, True)
+        ms_u, _ = timed(args.steps, False, use_graph)
+        ms_ue, _ = timed_e2e(args.steps, use_graph)
+        unpipelined = {"ms_per_step": ms_u / args.steps, "value": world * args.batch * args.points / (ms_u / args.steps / 1e3),
+                       "e2e_ms_per_step": ms_ue / args.steps}
+        cur["replay"] = replay
+        del ru
+        torch.cuda.empty_cache()
+
     ms_step = ms_total / args.steps
     pts = args.batch * args.points
     value = world * pts / (ms_step / 1e3)
@@ -495,6 +518,10 @@ def run_ours(args):
                     "host_loop": "inputs copied from pinned host memory and the loss copied back every step; the host "
                                  "reads step i's loss while step i+1 is queued (one step of lag)",
                     "blocking_ms_per_step": ms_e2e_blocking / e2e_steps},
+            "schedule": ("pipelined across steps: the FPS chain + first ball query of batch i+1 run on a side stream "
+                         "during step i (every step still executes one full FPS chain and one full feature pass)"
+                         if replay.prefetch else "every step starts with its own FPS chain"),
+            "unpipelined": unpipelined,
             "gpu_launches": int(launches), "mode": "cuda-graph replay of the whole step" if use_graph else "eager",
             "eager": eager, "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm,
             "kernels": kernels, "kernel_ms_per_step": round(total_ms, 3), "cpu_baseline": cpu_baseline,
@@ -520,6 +547,7 @@ def main():
     ap.add_argument("--grad-mb", type=float, default=166.3, help="flat gradient all-reduce per step (N>1): PointNeXt-XL FP32 grads")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-CUDA-kernels-on-this-GPU baseline")
+    ap.add_argument("--no-prefetch", action="store_true", help="do not pipeline the FPS chain of the next batch into the current step")
     ap.add_argument("--no-graph", action="store_true", help="time the eager (per-call Python) step instead of the CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":

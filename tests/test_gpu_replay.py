@@ -90,3 +90,30 @@ def test_full_size_grouping_roundtrip_linearity():
     rhs = (f.detach().double() * f.grad.double()).sum()
     # the sum of ~2e8 zero-mean terms cancels to O(sqrt(N)): compare on that scale (FP32 scatter-add rounding)
     assert abs(lhs - rhs) <= 1e-5 * terms.pow(2).sum().sqrt()
+
+
+def test_prefetch_pipeline_matches_unpipelined_batches():
+    """The cross-step pipeline (FPS chain + first ball query of batch i+1 computed during step i) returns, one
+    call late, exactly the losses of the unpipelined replay on the same batches — eager and as a CUDA graph."""
+    from amcontrast3d_b200.replay import PathReplay
+    batches = [scenes.batch_of_scenes(2, 4096, "surface", first_scene=s) for s in (0, 11, 23)]
+    dev = [(torch.from_numpy(x).cuda(), torch.from_numpy(l).cuda()) for x, l in batches]
+    ref = []
+    for s in (0, 11, 23):
+        r0 = PathReplay(batch=2, n_points=4096, k=16, first_scene=s, prefetch=False)
+        ref.append(r0.step().item())
+    r = PathReplay(batch=2, n_points=4096, k=16, first_scene=0, prefetch=True)
+    got = [r.step(*dev[1]).item(), r.step(*dev[2]).item(), r.step(*dev[0]).item(), r.step(*dev[1]).item()]
+    want = [ref[0], ref[1], ref[2], ref[0]]
+    for g, w in zip(got, want):
+        assert abs(g - w) <= 1e-6 * abs(w), (got, want)
+    # the same through a captured graph.  Kernels do not run while a graph is being captured, so after
+    # capture() the batch in flight is still the last one fed eagerly (batch 1)
+    r.capture(warmup=1)
+    pin = [(torch.from_numpy(x).pin_memory(), torch.from_numpy(l).pin_memory()) for x, l in batches]
+    g = [r.step_graph(*pin[2]).item(),         # -> loss of batch 1 (in flight), submits batch 2
+         r.step_graph(*pin[0]).item(),         # -> loss of batch 2
+         r.step_graph(*pin[1]).item(),         # -> loss of batch 0
+         r.step_graph(*pin[1]).item()]         # -> loss of batch 1
+    for got_i, want_i in zip(g, [ref[1], ref[2], ref[0], ref[1]]):
+        assert abs(got_i - want_i) <= 1e-6 * abs(want_i), (g, ref)
