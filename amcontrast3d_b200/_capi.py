@@ -48,6 +48,7 @@ SIGNATURES = {
     "amc3d_group_points_ws": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "amc3d_group_points_grad": [_I, _I, _I, _I, _I, _P, _P, _P, _P],
     "amc3d_group_points_grad_ws": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "amc3d_group_xyz_relative": [_I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P],
     "amc3d_gather_points": [_I, _I, _I, _I, _P, _P, _P, _P],
     "amc3d_gather_points_grad": [_I, _I, _I, _I, _P, _P, _P, _P],
     "amc3d_three_nn": [_I, _I, _I, _P, _P, _P, _P, _P],

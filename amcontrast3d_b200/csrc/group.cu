@@ -525,6 +525,36 @@ group_bwd_direct_kernel(int C, int N, int P, int cchunk, const float *__restrict
     for (int c = c0; c < c1; ++c, src += P, dst += N) atomicAdd(dst, __ldcs(src));
 }
 
+// QueryAndGroup's relative coordinates in one launch (group.py:244-249 of the reference composes them from a
+// transpose, a C = 3 grouping, a broadcast subtraction and a division by the radius):
+//     out[b,c,j,s] = (xyz[b, idx[b,j,s], c] - query[b,j,c]) * inv_radius
+// with inv_radius = 1.0f / (float)radius, which is how torch's CUDA true-division by a Python scalar is
+// evaluated (a * reciprocal(b), BinaryDivTrueKernel.cu) — so the result is bit-identical to the composition.
+// subtract == 0 leaves out the query, inv_radius == 0 the scaling.  xyz (B,N,3), query (B,M,3), out (B,3,M,ns).
+__global__ void __launch_bounds__(256)
+group_xyz_rel_kernel(int N, int M, int nsample, int subtract, float inv_radius, const float *__restrict__ xyz,
+                     const float *__restrict__ query, const int *__restrict__ idx, float *__restrict__ out) {
+    const int b = blockIdx.y;
+    const long long P = (long long)M * nsample;
+    const long long p = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (p >= P) return;
+    const int i = __ldg(idx + (long long)b * P + p);
+    const float *src = xyz + 3ll * ((long long)b * N + i);
+    float v[3] = {__ldg(src), __ldg(src + 1), __ldg(src + 2)};
+    if (subtract) {
+        const float *q = query + 3ll * ((long long)b * M + p / nsample);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = __fsub_rn(v[c], __ldg(q + c));
+    }
+    if (inv_radius != 0.f) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = __fmul_rn(v[c], inv_radius);
+    }
+    float *o = out + 3ll * b * P + p;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c * P] = v[c];
+}
+
 // three_interpolate: out[b,c,i] = w0*f[i0] + w1*f[i1] + w2*f[i2], contracted exactly like nvcc
 // contracts the reference expression (interpolate_gpu.cu:103; verified in its sm_100 SASS):
 //     fma(w2,f2, fma(w0,f0, fl(w1*f1)))
@@ -693,6 +723,18 @@ extern "C" int amc3d_group_points_grad(int b, int c, int n, int npoints, int nsa
                                        const float *grad_out, const int *idx, float *grad_points,
                                        void *stream) {
     return amc3d_group_points_grad_ws(b, c, n, npoints, nsample, grad_out, idx, grad_points, nullptr, stream);
+}
+
+extern "C" int amc3d_group_xyz_relative(int b, int n, int m, int nsample, int subtract, float inv_radius,
+                                        const float *xyz, const float *query, const int *idx, float *out,
+                                        void *stream) {
+    AMC3D_REQUIRE(b >= 0 && n >= 0 && m >= 0 && nsample >= 0, AMC3D_EINVAL, "group_xyz_relative: negative size");
+    AMC3D_REQUIRE(b <= 65535, AMC3D_ELIMIT, "group_xyz_relative: batch %d > 65535", b);
+    const long long P = (long long)m * nsample;
+    if (b == 0 || P == 0) return 0;
+    dim3 grid((unsigned)div_up_ll(P, 256), b);
+    group_xyz_rel_kernel<<<grid, 256, 0, as_stream(stream)>>>(n, m, nsample, subtract, inv_radius, xyz, query, idx, out);
+    return check_launch("group_xyz_relative");
 }
 
 // gather_points = group_points with nsample = 1

@@ -77,6 +77,20 @@ class BallQuery(Function):
 ball_query = BallQuery.apply
 
 
+def _group_xyz_relative(support_xyz, query_xyz, idx, subtract, radius):
+    import numpy as np
+
+    from .. import _capi
+    B, N, _ = support_xyz.shape
+    M, ns = idx.shape[1], idx.shape[2]
+    out = torch.empty((B, 3, M, ns), dtype=torch.float32, device=support_xyz.device)
+    inv = float(np.float32(1.0) / np.float32(radius)) if radius is not None else 0.0
+    with _capi.guard(support_xyz):
+        _capi.call("amc3d_group_xyz_relative", B, N, M, ns, int(bool(subtract)), inv, _capi.ptr(support_xyz),
+                   _capi.ptr(query_xyz), _capi.ptr(idx), _capi.ptr(out), _capi.stream(support_xyz))
+    return out
+
+
 class QueryAndGroup(nn.Module):
     """ref: group.py:206-255.  forward(query_xyz (B,M,3), support_xyz (B,N,3), features (B,C,N))
     -> (grouped relative xyz (B,3,M,ns), grouped features (B,C,M,ns))."""
@@ -102,11 +116,21 @@ class QueryAndGroup(nn.Module):
             idx = ball_query(self.radius, self.nsample, support_xyz, query_xyz)
         if self.return_only_idx:
             return idx
-        grouped_xyz = grouping_operation(support_xyz.transpose(1, 2).contiguous(), idx)
-        if self.relative_xyz:
-            grouped_xyz = grouped_xyz - query_xyz.transpose(1, 2).unsqueeze(-1)
-            if self.normalize_dp:
-                grouped_xyz /= self.radius
+        plain = not (self.normalize_by_std or self.normalize_by_allstd or self.normalize_by_allstd2)
+        if (plain and support_xyz.is_cuda and not support_xyz.requires_grad and not query_xyz.requires_grad
+                and support_xyz.dtype == torch.float32 and query_xyz.dtype == torch.float32
+                and support_xyz.is_contiguous() and query_xyz.is_contiguous() and idx.is_contiguous()):
+            # coordinates carry no gradient here (they never do in PointNeXt): the transpose, the C = 3
+            # grouping, the subtraction and the division of the reference collapse into one kernel with
+            # bit-identical results (torch divides by a Python scalar as a * (1/r) on CUDA)
+            grouped_xyz = _group_xyz_relative(support_xyz, query_xyz, idx, self.relative_xyz,
+                                              self.radius if (self.relative_xyz and self.normalize_dp) else None)
+        else:
+            grouped_xyz = grouping_operation(support_xyz.transpose(1, 2).contiguous(), idx)
+            if self.relative_xyz:
+                grouped_xyz = grouped_xyz - query_xyz.transpose(1, 2).unsqueeze(-1)
+                if self.normalize_dp:
+                    grouped_xyz /= self.radius
         grouped_features = grouping_operation(features, idx) if features is not None else None
         return grouped_xyz, grouped_features
 

@@ -80,6 +80,16 @@ int amc3d_group_points_grad_ws(int b, int c, int n, int npoints, int nsample,
                                const float *grad_out, const int *idx, float *grad_points,
                                float *workspace, void *stream);
 
+/* QueryAndGroup's relative coordinates in one launch:
+ *   out[b,c,j,s] = (xyz[b,idx[b,j,s],c] - query[b,j,c]) * inv_radius ,  out (B,3,M,nsample)
+ * xyz (B,N,3) and query (B,M,3) in their native layout (no transpose), inv_radius = 1.0f/(float)radius —
+ * bit-identical to the reference's composition grouping_operation(xyz^T, idx) - query, / radius as torch
+ * evaluates it on CUDA.  subtract == 0: no query term; inv_radius == 0: no scaling.
+ * ref: models/layers/group.py:244-249 (QueryAndGroup.forward) */
+int amc3d_group_xyz_relative(int b, int n, int m, int nsample, int subtract, float inv_radius,
+                             const float *xyz, const float *query, const int *idx, float *out,
+                             void *stream);
+
 /* out[b,c,j] = points[b,c,idx[b,j]].  ref: sampling.cpp:16, sampling_gpu.cu:33 */
 int amc3d_gather_points(int b, int c, int n, int npoints, const float *points,
                         const int *idx, float *out, void *stream);

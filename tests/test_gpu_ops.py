@@ -276,6 +276,32 @@ def test_query_and_group_module():
     assert np.array_equal(fj.cpu().numpy(), oo.group_points(feats, idx))
 
 
+@pytest.mark.parametrize("relative,normalize,radius", [(True, True, 0.15), (True, True, 0.1), (True, True, 1.6),
+                                                       (True, False, 0.2), (False, False, 0.2)])
+def test_fused_relative_xyz_is_bit_identical_to_the_composition(relative, normalize, radius):
+    """QueryAndGroup's one-kernel relative coordinates == transpose + grouping + subtraction + division as torch
+    evaluates them on the device (group.py:244-249 of the reference), bit for bit."""
+    from amcontrast3d_b200.layers import QueryAndGroup, ball_query, grouping_operation
+    xyz, _ = scenes.batch_of_scenes(3, 4000, "surface", first_scene=15)
+    sup, qry = _t(xyz), _t(np.ascontiguousarray(xyz[:, :1000]))
+    grouper = QueryAndGroup(radius, 32, relative_xyz=relative, normalize_dp=normalize)
+    dp, fj = grouper(qry, sup, None)
+    assert fj is None
+    idx = ball_query(radius, 32, sup, qry)
+    ref = grouping_operation(sup.transpose(1, 2).contiguous(), idx)
+    if relative:
+        ref = ref - qry.transpose(1, 2).unsqueeze(-1)
+        if normalize:
+            ref /= radius
+    assert torch.equal(dp, ref)
+    # coordinates that require grad take the differentiable composition
+    sup_g = sup.clone().requires_grad_(True)
+    dp_g, _ = grouper(qry, sup_g, None)
+    assert torch.equal(dp_g.detach(), ref)
+    dp_g.sum().backward()
+    assert sup_g.grad is not None
+
+
 def test_pointops_grouping_packed_layout():
     from amcontrast3d_b200 import pointops
     rng = np.random.default_rng(5)
