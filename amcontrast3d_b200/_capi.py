@@ -48,6 +48,7 @@ SIGNATURES = {
     "amc3d_group_points_ws": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "amc3d_group_points_grad": [_I, _I, _I, _I, _I, _P, _P, _P, _P],
     "amc3d_group_points_grad_ws": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "amc3d_group_points_grad_ws_set": [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "amc3d_group_xyz_relative": [_I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P],
     "amc3d_gather_points": [_I, _I, _I, _I, _P, _P, _P, _P],
     "amc3d_gather_points_grad": [_I, _I, _I, _I, _P, _P, _P, _P],
@@ -56,6 +57,7 @@ SIGNATURES = {
     "amc3d_three_interpolate_grad": [_I, _I, _I, _I, _P, _P, _P, _P, _P],
     "amc3d_three_interpolate_ws": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "amc3d_three_interpolate_grad_ws": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
+    "amc3d_three_interpolate_grad_ws_set": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "amc3d_knnquery": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "amc3d_knnquery_order": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "amc3d_grouping_forward": [_I, _I, _I, _P, _P, _P, _P],
@@ -122,11 +124,11 @@ PROFILE = None
 def _kernels_in(name: str, args) -> int:
     if name == "amc3d_group_points_ws":
         return 2 if args[-2] else 1            # transpose + gather with a workspace
-    if name == "amc3d_group_points_grad_ws":
+    if name in ("amc3d_group_points_grad_ws", "amc3d_group_points_grad_ws_set"):
         return 2 if args[-2] else 1            # scatter + transpose-accumulate (plus a memset)
     if name == "amc3d_three_interpolate_ws":
         return 2 if args[-2] else 1            # transpose + interpolate
-    if name == "amc3d_three_interpolate_grad_ws":
+    if name in ("amc3d_three_interpolate_grad_ws", "amc3d_three_interpolate_grad_ws_set"):
         return 2 if args[-2] else 1            # scatter + transpose-accumulate (plus a memset)
     if name == "amc3d_refine_backward":
         return 2

@@ -659,7 +659,8 @@ static int group_impl() {
 }
 
 static int group_common(bool fwd, int b, int c, int n, long long P, const float *src, const int *idx,
-                        float *dst, float *workspace, cudaStream_t st, const char *what, int nsample = 0) {
+                        float *dst, float *workspace, cudaStream_t st, const char *what, int nsample = 0,
+                        bool overwrite = false) {
     if (b == 0 || c == 0 || P == 0) return 0;
     AMC3D_REQUIRE(b <= 65535, AMC3D_ELIMIT, "%s: batch %d > 65535", what, b);
     AMC3D_REQUIRE(P < (1ll << 31), AMC3D_ELIMIT, "%s: npoints*nsample too large", what);
@@ -685,9 +686,11 @@ static int group_common(bool fwd, int b, int c, int n, long long P, const float 
                 group_bwd_tma_kernel<false><<<grid, 256, smem, st>>>(c, n, (int)P, 0, src, idx, workspace);
             else
                 group_bwd_cl_kernel<<<grid, GRP_WARPS * 32, 0, st>>>(c, n, (int)P, src, idx, workspace);
-            launch_transpose<true>(b, n, c, workspace, dst, st);   // (B,N,C) -> += (B,C,N)
+            if (overwrite) launch_transpose<false>(b, n, c, workspace, dst, st);   // (B,N,C) -> (B,C,N)
+            else launch_transpose<true>(b, n, c, workspace, dst, st);              // (B,N,C) -> += (B,C,N)
         }
     } else {
+        if (!fwd && overwrite) cudaMemsetAsync(dst, 0, sizeof(float) * (size_t)b * n * c, st);
         const long long bx = div_up_ll(P, 256);
         const int cchunk = pick_cchunk(c, bx * b);
         dim3 grid((unsigned)bx, div_up(c, cchunk), b);
@@ -719,6 +722,15 @@ extern "C" int amc3d_group_points_grad_ws(int b, int c, int n, int npoints, int 
     return group_common(false, b, c, n, (long long)npoints * nsample, grad_out, idx, grad_points,
                         workspace, as_stream(stream), "group_points_grad", nsample);
 }
+extern "C" int amc3d_group_points_grad_ws_set(int b, int c, int n, int npoints, int nsample,
+                                              const float *grad_out, const int *idx, float *grad_points,
+                                              float *workspace, void *stream) {
+    AMC3D_REQUIRE(b >= 0 && c >= 0 && n >= 0 && npoints >= 0 && nsample >= 0, AMC3D_EINVAL,
+                  "group_points_grad: negative size");
+    return group_common(false, b, c, n, (long long)npoints * nsample, grad_out, idx, grad_points,
+                        workspace, as_stream(stream), "group_points_grad", nsample, true);
+}
+
 extern "C" int amc3d_group_points_grad(int b, int c, int n, int npoints, int nsample,
                                        const float *grad_out, const int *idx, float *grad_points,
                                        void *stream) {
@@ -777,9 +789,25 @@ extern "C" int amc3d_three_interpolate(int b, int c, int m, int n, const float *
     return amc3d_three_interpolate_ws(b, c, m, n, points, idx, weight, out, nullptr, stream);
 }
 
+static int interp_grad_common(int b, int c, int n, int m, const float *grad_out, const int *idx,
+                              const float *weight, float *grad_points, float *workspace, void *stream,
+                              bool overwrite);
+
 extern "C" int amc3d_three_interpolate_grad_ws(int b, int c, int n, int m, const float *grad_out,
                                                const int *idx, const float *weight, float *grad_points,
                                                float *workspace, void *stream) {
+    return interp_grad_common(b, c, n, m, grad_out, idx, weight, grad_points, workspace, stream, false);
+}
+
+extern "C" int amc3d_three_interpolate_grad_ws_set(int b, int c, int n, int m, const float *grad_out,
+                                                   const int *idx, const float *weight, float *grad_points,
+                                                   float *workspace, void *stream) {
+    return interp_grad_common(b, c, n, m, grad_out, idx, weight, grad_points, workspace, stream, true);
+}
+
+static int interp_grad_common(int b, int c, int n, int m, const float *grad_out, const int *idx,
+                              const float *weight, float *grad_points, float *workspace, void *stream,
+                              bool overwrite) {
     AMC3D_REQUIRE(b >= 0 && c >= 0 && m >= 0 && n >= 0, AMC3D_EINVAL, "three_interpolate_grad: negative size");
     AMC3D_REQUIRE(b <= 65535, AMC3D_ELIMIT, "three_interpolate_grad: batch %d > 65535", b);
     if (b == 0 || c == 0 || n == 0) return 0;
@@ -789,9 +817,11 @@ extern "C" int amc3d_three_interpolate_grad_ws(int b, int c, int n, int m, const
         dim3 grid(div_up(n, TP), div_up(c, TC), b);
         const size_t smem = (TC * BWD_LD + 32 + TP * 6) * sizeof(float);
         interp_bwd_tma_kernel<<<grid, 256, smem, st>>>(c, n, m, grad_out, idx, weight, workspace);
-        launch_transpose<true>(b, m, c, workspace, grad_points, st);   // (B,m,C) -> += (B,C,m)
+        if (overwrite) launch_transpose<false>(b, m, c, workspace, grad_points, st);   // (B,m,C) -> (B,C,m)
+        else launch_transpose<true>(b, m, c, workspace, grad_points, st);              // (B,m,C) -> += (B,C,m)
         return check_launch("three_interpolate_grad");
     }
+    if (overwrite) cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)b * m * c, as_stream(stream));
     const int bx = div_up(n, 256);
     const int cchunk = pick_cchunk(c, (long long)bx * b);
     dim3 grid(bx, div_up(c, cchunk), b);

@@ -38,9 +38,9 @@ class GroupingOperation(Function):
     def backward(ctx, grad_out: torch.Tensor) -> Tuple[torch.Tensor, None]:
         idx, N = ctx.for_backwards
         B, C, npoint, nsample = grad_out.size()
-        grad_features = torch.zeros((B, C, N), dtype=torch.float32, device=grad_out.device)
-        pointnet2_cuda.group_points_grad_wrapper(B, C, N, npoint, nsample, grad_out.contiguous(), idx,
-                                                 grad_features)
+        # the reference zero-fills and accumulates (group.py:111-113); writing the result is the same thing
+        grad_features = torch.empty((B, C, N), dtype=torch.float32, device=grad_out.device)
+        pointnet2_cuda.group_points_grad_set(B, C, N, npoint, nsample, grad_out.contiguous(), idx, grad_features)
         return grad_features, None
 
 

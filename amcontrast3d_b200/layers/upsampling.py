@@ -57,9 +57,8 @@ class ThreeInterpolate(Function):
     def backward(ctx, grad_out: torch.Tensor):
         idx, weight, m = ctx.three_interpolate_for_backward
         B, c, n = grad_out.size()
-        grad_features = torch.zeros((B, c, m), dtype=torch.float32, device=grad_out.device)
-        pointnet2_cuda.three_interpolate_grad_wrapper(B, c, n, m, grad_out.contiguous(), idx, weight,
-                                                      grad_features)
+        grad_features = torch.empty((B, c, m), dtype=torch.float32, device=grad_out.device)
+        pointnet2_cuda.three_interpolate_grad_set(B, c, n, m, grad_out.contiguous(), idx, weight, grad_features)
         return grad_features, None, None
 
 

@@ -50,6 +50,24 @@ def group_points_grad_wrapper(b, c, n, npoints, nsample, grad_out, idx, grad_poi
     return 1
 
 
+def group_points_grad_set(b, c, n, npoints, nsample, grad_out, idx, grad_points):
+    """Not in the reference module: group_points_grad_wrapper for an UNINITIALISED grad_points (written, not
+    accumulated) — what layers.GroupingOperation.backward uses, saving the zero-fill and one read of it."""
+    with _guard(grad_out):
+        ws = _workspace(grad_out, b * n * c) if c >= 8 else None
+        _capi.call("amc3d_group_points_grad_ws_set", b, c, n, npoints, nsample, ptr(grad_out), ptr(idx),
+                   ptr(grad_points), ptr(ws), stream(grad_out))
+    return 1
+
+
+def three_interpolate_grad_set(b, c, n, m, grad_out, idx, weight, grad_points):
+    """Not in the reference module: three_interpolate_grad_wrapper for an uninitialised grad_points."""
+    with _guard(grad_out):
+        ws = _workspace(grad_out, b * m * c) if c >= 8 else None
+        _capi.call("amc3d_three_interpolate_grad_ws_set", b, c, n, m, ptr(grad_out), ptr(idx), ptr(weight),
+                   ptr(grad_points), ptr(ws), stream(grad_out))
+
+
 def gather_points_wrapper(b, c, n, npoints, points, idx, out):
     """ref: sampling.cpp:16 gather_points_wrapper_fast"""
     with _guard(points):

@@ -249,13 +249,13 @@ def algorithmic_work(name, a):
     if name in ("amc3d_group_points_ws", "amc3d_group_points"):
         b, c, n, npnt, ns = a[:5]
         return "byte", 4.0 * b * (c * npnt * ns + c * n + npnt * ns)
-    if name in ("amc3d_group_points_grad_ws", "amc3d_group_points_grad"):
+    if name in ("amc3d_group_points_grad_ws", "amc3d_group_points_grad", "amc3d_group_points_grad_ws_set"):
         b, c, n, npnt, ns = a[:5]
         return "byte", 4.0 * b * (c * npnt * ns + 2 * c * n + npnt * ns)
     if name in ("amc3d_three_interpolate", "amc3d_three_interpolate_ws"):
         b, c, m, n = a[:4]
         return "byte", 4.0 * b * (c * n + c * m + 6 * n)
-    if name in ("amc3d_three_interpolate_grad", "amc3d_three_interpolate_grad_ws"):
+    if name in ("amc3d_three_interpolate_grad", "amc3d_three_interpolate_grad_ws", "amc3d_three_interpolate_grad_ws_set"):
         b, c, n, m = a[:4]
         return "byte", 4.0 * b * (c * n + 2 * c * m + 6 * n)
     return None, 0.0
@@ -452,7 +452,15 @@ def run_ours(args):
         return
 
     # kernel accounting (untimed extra step) and the CPU baseline (N = 1 only)
-    agg = profile_step(replay)
+    # per-kernel accounting on a single-stream pass (no geometry streams, no pipeline): with the side streams
+    # active, a call's event-to-event time also contains whatever ran next to it
+    serial = PathReplay(batch=args.batch, n_points=args.points, device=dev, k=args.k, rank=rank,
+                        geometry_stream=False, prefetch=False)
+    for _ in range(2):
+        serial.step()
+    agg = profile_step(serial)
+    del serial
+    torch.cuda.empty_cache()
     total_ms = sum(d["ms"] for d in agg.values())
     hbm_peak, peak_src = measured_peaks()
     fp32_peak = fp32_peak_tflops()
@@ -471,7 +479,8 @@ def run_ours(args):
     if os.path.exists(tpath):
         traffic = json.load(open(tpath))
     # the dominant HBM-bound kernel: the larger of the two TMA-staged grouping kernels (19 launches each per step)
-    KERNEL_OF = {"amc3d_group_points_ws": "group_fwd_tma_kernel", "amc3d_group_points_grad_ws": "group_bwd_tma_kernel"}
+    KERNEL_OF = {"amc3d_group_points_ws": "group_fwd_tma_kernel", "amc3d_group_points_grad_ws": "group_bwd_tma_kernel",
+                 "amc3d_group_points_grad_ws_set": "group_bwd_tma_kernel"}
     hbm_rows = [r for r in kernels if r["entry"] in KERNEL_OF and "gbs" in r]
     roofline = None
     if hbm_rows:
@@ -484,7 +493,8 @@ def run_ours(args):
                     "ms_per_launch": round(per_launch_ms, 4),
                     "algorithmic_bytes_per_launch": round(agg[dom["entry"]]["byte"] / dom["calls"]),
                     "traffic": t,
-                    "note": "per-launch figures are means over the step's launches of this entry point (transpose / "
+                    "note": "measured on a single-stream pass of the step; per-launch figures are means over the step's "
+                            "launches of this entry point (transpose / "
                             "memset / accumulate launches of the call included in the time); FPS, the largest single "
                             "share, is latency-bound and reported in kernels[] as us per pick"}
     roofline_hbm = [{"kernel": r["entry"], "achieved": r["gbs"], "peak": hbm_peak, "unit": "GB/s",

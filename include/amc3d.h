@@ -90,6 +90,12 @@ int amc3d_group_xyz_relative(int b, int n, int m, int nsample, int subtract, flo
                              const float *xyz, const float *query, const int *idx, float *out,
                              void *stream);
 
+/* amc3d_group_points_grad_ws for a caller that does NOT need the accumulate semantics: grad_points is
+ * written, not added to, so it need not be zero-filled (saves the caller's memset and one read of it). */
+int amc3d_group_points_grad_ws_set(int b, int c, int n, int npoints, int nsample,
+                                   const float *grad_out, const int *idx, float *grad_points,
+                                   float *workspace, void *stream);
+
 /* out[b,c,j] = points[b,c,idx[b,j]].  ref: sampling.cpp:16, sampling_gpu.cu:33 */
 int amc3d_gather_points(int b, int c, int n, int npoints, const float *points,
                         const int *idx, float *out, void *stream);
@@ -123,6 +129,11 @@ int amc3d_three_interpolate_grad(int b, int c, int n, int m, const float *grad_o
 int amc3d_three_interpolate_grad_ws(int b, int c, int n, int m, const float *grad_out,
                                     const int *idx, const float *weight, float *grad_points,
                                     float *workspace, void *stream);
+
+/* As amc3d_three_interpolate_grad_ws, but grad_points is written, not added to (no zero-fill needed). */
+int amc3d_three_interpolate_grad_ws_set(int b, int c, int n, int m, const float *grad_out,
+                                        const int *idx, const float *weight, float *grad_points,
+                                        float *workspace, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * pointops family: packed (n,3) xyz / (n,c) features with cumulative i32 `offset` ends

@@ -36,6 +36,8 @@ for r in rows[2:]:
             t = float(r[it].replace(",", ""))
             a[2] += t * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(units[it], 1.0)
 res = {e: round(a[1] / a[0]) for e, a in agg.items()}
+if "amc3d_group_points_grad_ws" in res:      # the autograd path calls the overwrite variant of the same kernel
+    res["amc3d_group_points_grad_ws_set"] = res["amc3d_group_points_grad_ws"]
 json.dump(res, open(out_json, "w"), indent=1)
 print("| entry point | launches | mean dram bytes / launch | mean kernel us |")
 print("|---|---:|---:|---:|")
