@@ -59,14 +59,13 @@ class PathReplay:
         self._geo = None
         self._geo2 = None
         self._am_geometry = None
-        # prefetch: a software pipeline across steps.  The FPS chain of a batch (and the first ball query,
-        # which everything at level 1 waits for) depends on its coordinates only, so it is computed one step
-        # EARLY, on a side stream, while the previous batch's feature path and backward keep HBM busy — the
-        # way a data loader prefetches.  Every step still runs one full FPS chain and one full feature pass;
-        # the ~1.7 ms of start-up latency at the head of the step disappears from the critical path.
+        # prefetch: a software pipeline across steps.  The geometry of a batch (FPS chain, ball queries,
+        # three_nn, the loss's labels / kNN / ambiguity) depends on its coordinates and labels only, so it is
+        # computed one step EARLY, on side streams, while the previous batch's feature path and backward keep
+        # HBM busy — the way a data loader prefetches.  Every step still runs one full geometry pass and one
+        # full feature pass; the feature path no longer waits for any search.
         self.prefetch = prefetch and self.geometry_stream
-        self._geoN = None
-        self._pf = None           # {'p': [p1..p4] static, 'sa1': static idx, 'next': (tmp p list, tmp sa1)}
+        self._pf = None           # {'cur': static geometry of the batch in flight, 'next': this step's}
         xyz, labels = scenes.batch_of_scenes(batch, n_points, kind, rank=rank, first_scene=first_scene,
                                              num_classes=num_classes,
                                              ignore_fraction=0.05 if ignore_index is not None else 0.0)
@@ -224,91 +223,112 @@ class PathReplay:
             q.append(torch.gather(q[l - 1], 1, idx.unsqueeze(-1).expand(-1, -1, 3)).contiguous())
         return q
 
-    def _forward_prefetch(self, xyz=None, labels=None):
-        """Pipelined schedule: `xyz` / `labels` (if given) are the NEXT batch; the batch whose FPS chain was
-        prefetched during the previous call goes through the feature path now."""
+    def _geometry(self, xyz, labels, enc, aux):
+        """Everything of one batch that depends on coordinates and labels only — FPS chain, all ball queries,
+        the three_nn searches and the loss's label / kNN / ambiguity geometry — issued on the streams `enc`
+        (encoder geometry) and `aux` (loss geometry, which only waits for the points of its stage)."""
         from .layers import ball_query, three_nn
+        arch, nlev = self.arch, len(self.arch["blocks"])
+        G = {"p": [], "sa": [None], "la": [None], "nn3": [None] * nlev, "am": None}
+        ev_pts = [None] * nlev
+        with torch.cuda.stream(enc):
+            q = [xyz]
+            for l in range(1, nlev):
+                idx = furthest_point_sample(q[l - 1], self.n[l]).long()
+                q.append(torch.gather(q[l - 1], 1, idx.unsqueeze(-1).expand(-1, -1, 3)).contiguous())
+                ev_pts[l] = torch.cuda.Event()
+                ev_pts[l].record(enc)
+            G["p"] = q[1:]
+            for l in range(1, nlev):
+                sa_idx, la_idx = None, []
+                if self.with_grouping:
+                    sa_idx = ball_query(self.sa[l].radius, self.sa[l].nsample, q[l - 1], q[l])
+                    la_idx = [ball_query(self.la[l].radius, self.la[l].nsample, q[l], q[l])
+                              for _ in range(arch["blocks"][l] - 1)]
+                G["sa"].append(sa_idx)
+                G["la"].append(la_idx)
+            for l in range(nlev - 1, 0, -1):
+                G["nn3"][l] = three_nn(q[l - 1], q[l])
+        if self.with_loss:
+            with torch.cuda.stream(aux):
+                pts, am = [], []
+                sl = {"down": pts, "up": pts}
+                for s in range(4):
+                    if s > 0:
+                        aux.wait_event(ev_pts[s])
+                    pts.append({"p_out": q[s].reshape(-1, 3), "offset": self._offsets[s]})
+                    am.append(self.head.precompute_geometry(s, sl, labels.reshape(-1), self.num_classes,
+                                                            self.ignore_index, self.args))
+                G["am"] = am
+        return G
+
+    _AM_KEYS = ("knn_idx", "posbits", "cnt", "a", "stats", "cls", "order")
+
+    def _copy_geometry(self, dst, src):
+        """dst <- src for every tensor a later step reads (the static copy the captured graph is bound to)."""
+        for d, s_ in zip(dst["p"], src["p"]):
+            d.copy_(s_)
+        for l in range(1, len(dst["sa"])):
+            if dst["sa"][l] is not None:
+                dst["sa"][l].copy_(src["sa"][l])
+            for d, s_ in zip(dst["la"][l], src["la"][l]):
+                d.copy_(s_)
+        for d, s_ in zip(dst["nn3"], src["nn3"]):
+            if d is not None:
+                d[0].copy_(s_[0])
+                d[1].copy_(s_[1])
+        if dst["am"] is not None:
+            for d, s_ in zip(dst["am"], src["am"]):
+                for k in self._AM_KEYS:
+                    if d.get(k) is not None:
+                        d[k].copy_(s_[k])
+
+    def _forward_prefetch(self, xyz=None, labels=None):
+        """Pipelined schedule: `xyz` / `labels` (if given) are the NEXT batch, whose whole geometry is computed
+        on side streams during this call; the batch whose geometry was computed during the previous call goes
+        through the feature path now, without waiting for any search."""
         arch, nlev = self.arch, len(self.arch["blocks"])
         main = torch.cuda.current_stream(self.device)
         if self._pf is None:
-            # prologue (eager, once): buffers for the next batch and the current batch's FPS chain
-            self.d_xyz_next, self.d_labels_next = self.d_xyz.clone(), self.d_labels.clone()
-            q = self._fps_chain(self.d_xyz)
-            sa1 = ball_query(self.sa[1].radius, self.sa[1].nsample, q[0], q[1]) if self.with_grouping else None
-            self._pf = {"p": q[1:], "sa1": sa1, "next": None}
-            for name in ("_geo", "_geo2", "_geoN"):
+            # prologue (eager, once): streams, buffers for the next batch, the current batch's geometry
+            for name in ("_geo", "_geo2"):
                 setattr(self, name, torch.cuda.Stream(device=self.device))
+            self.d_xyz_next, self.d_labels_next = self.d_xyz.clone(), self.d_labels.clone()
+            for st in (self._geo, self._geo2):
+                st.wait_stream(main)
+            self._pf = {"cur": self._geometry(self.d_xyz, self.d_labels, self._geo, self._geo2), "next": None}
+            main.wait_stream(self._geo)
+            main.wait_stream(self._geo2)
         if xyz is not None:
             self.d_xyz_next.copy_(xyz, non_blocking=True)
         if labels is not None:
             self.d_labels_next.copy_(labels, non_blocking=True)
-        geo, geo2, geoN = self._geo, self._geo2, self._geoN
-        for st in (geo, geo2, geoN):
-            st.wait_stream(main)                                    # fork
-        # next batch: FPS chain + the first ball query, nothing on the current step waits for this
-        with torch.cuda.stream(geoN):
-            q = self._fps_chain(self.d_xyz_next)
-            sa1n = ball_query(self.sa[1].radius, self.sa[1].nsample, q[0], q[1]) if self.with_grouping else None
-            self._pf["next"] = (q[1:], sa1n)
-        # current batch: its points exist already, so every search can start at once
-        p = [self.d_xyz] + self._pf["p"]
-        labels_cur = self.d_labels
+        geo, geo2 = self._geo, self._geo2
+        geo.wait_stream(main)                                       # fork
+        geo2.wait_stream(main)
+        self._pf["next"] = self._geometry(self.d_xyz_next, self.d_labels_next, geo, geo2)
+        # the current batch: every index it needs exists already
+        G = self._pf["cur"]
+        p = [self.d_xyz] + G["p"]
         outs = []
-        ev_lvl, ev_up, bq_sa, bq_la, nn3 = [None], [None] * nlev, [None], [None], [None] * nlev
-        with torch.cuda.stream(geo):
-            for l in range(1, nlev):
-                sa_idx, la_idx = None, []
-                if self.with_grouping:
-                    sa_idx = self._pf["sa1"] if l == 1 else ball_query(self.sa[l].radius, self.sa[l].nsample, p[l - 1], p[l])
-                    la_idx = [ball_query(self.la[l].radius, self.la[l].nsample, p[l], p[l])
-                              for _ in range(arch["blocks"][l] - 1)]
-                bq_sa.append(sa_idx)
-                bq_la.append(la_idx)
-                ev = torch.cuda.Event()
-                ev.record(geo)
-                ev_lvl.append(ev)
-            for l in range(nlev - 1, 0, -1):
-                nn3[l] = three_nn(p[l - 1], p[l])
-                ev_up[l] = torch.cuda.Event()
-                ev_up[l].record(geo)
-        if self.with_loss:
-            with torch.cuda.stream(geo2):
-                pts, self._am_geometry = [], []
-                for s in range(4):
-                    pts.append({"p_out": p[s].reshape(-1, 3), "offset": self._offsets[s]})
-                    sl = {"down": pts, "up": pts}
-                    self._am_geometry.append(self.head.precompute_geometry(
-                        s, sl, labels_cur.reshape(-1), self.num_classes, self.ignore_index, self.args))
         for l in range(1, nlev):
             if self.with_grouping:
-                # the level-1 SetAbstraction grouping needs no search of this step at all
-                dp, fj = self.sa[l](p[l], p[l - 1], self.F[l - 1], idx=bq_sa[l]) if l == 1 else (None, None)
-                if l == 1:
-                    outs.append(fj)
-            main.wait_event(ev_lvl[l])
-            if self.with_grouping:
-                if l > 1:
-                    dp, fj = self.sa[l](p[l], p[l - 1], self.F[l - 1], idx=bq_sa[l])
-                    outs.append(fj)
+                dp, fj = self.sa[l](p[l], p[l - 1], self.F[l - 1], idx=G["sa"][l])
+                outs.append(fj)
                 for i in range(arch["blocks"][l] - 1):
-                    dp, fj = self.la[l](p[l], p[l], self.F[l], idx=bq_la[l][i])
+                    dp, fj = self.la[l](p[l], p[l], self.F[l], idx=G["la"][l][i])
                     outs.append(fj)
         for l in range(nlev - 1, 0, -1):
-            main.wait_event(ev_up[l])
-            outs.append(three_interpolation(p[l - 1], p[l], self.F[l], nn=nn3[l]))
-        main.wait_stream(geo)                                       # join (geoN is joined after the backward)
-        main.wait_stream(geo2)
-        return self._loss_tail(p, labels_cur), outs
+            outs.append(three_interpolation(p[l - 1], p[l], self.F[l], nn=G["nn3"][l]))
+        self._am_geometry = G["am"]
+        return self._loss_tail(p, self.d_labels), outs
 
     def _rotate_prefetch(self):
-        """End of a pipelined step: the prefetched chain becomes the current batch's."""
+        """End of a pipelined step: the geometry computed for the next batch becomes the current batch's."""
         main = torch.cuda.current_stream(self.device)
-        main.wait_stream(self._geoN)
-        q, sa1n = self._pf["next"]
-        for dst, src in zip(self._pf["p"], q):
-            dst.copy_(src)
-        if sa1n is not None:
-            self._pf["sa1"].copy_(sa1n)
+        main.wait_stream(self._geo)                                 # join
+        main.wait_stream(self._geo2)
+        self._copy_geometry(self._pf["cur"], self._pf["next"])
         self.d_xyz.copy_(self.d_xyz_next)
         self.d_labels.copy_(self.d_labels_next)
         self._pf["next"] = None

@@ -528,8 +528,9 @@ def run_ours(args):
                     "host_loop": "inputs copied from pinned host memory and the loss copied back every step; the host "
                                  "reads step i's loss while step i+1 is queued (one step of lag)",
                     "blocking_ms_per_step": ms_e2e_blocking / e2e_steps},
-            "schedule": ("pipelined across steps: the FPS chain + first ball query of batch i+1 run on a side stream "
-                         "during step i (every step still executes one full FPS chain and one full feature pass)"
+            "schedule": ("pipelined across steps: the geometry of batch i+1 (FPS chain, ball queries, three_nn, loss "
+                         "labels/kNN/ambiguity) runs on side streams during the feature pass + backward of batch i "
+                         "(every step still executes one full geometry pass and one full feature pass)"
                          if replay.prefetch else "every step starts with its own FPS chain"),
             "unpipelined": unpipelined,
             "gpu_launches": int(launches), "mode": "cuda-graph replay of the whole step" if use_graph else "eager",
