@@ -119,6 +119,22 @@ def test_knn_full_size_properties():
                np.array([1024], dtype=np.int32), sqrt=False)
 
 
+def test_knn_whole_room_size():
+    """eval-time shape (metrics.py:160-184 runs the kNN on a whole room as ONE segment): 400 000 points, checked
+    through sortedness, the self match, and 512 sampled queries against the oracle's brute force"""
+    from amcontrast3d_b200 import _amloss
+    xyz, _ = scenes.volume_scene(400000, seed=21)
+    n = xyz.shape[0]
+    o = np.array([n], dtype=np.int32)
+    idx, d2 = _amloss.knn_raw(16, _t(xyz), None, _t(o), _t(o))
+    idx, d2 = idx.cpu().numpy(), d2.cpu().numpy()
+    assert (np.diff(d2, axis=1) >= 0).all()
+    assert (d2[:, 0] == 0).all() and (idx[:, 0] == np.arange(n)).mean() > 0.999
+    sample = np.random.default_rng(1).choice(n, 512, replace=False)
+    _check_knn(idx[sample], d2[sample], 16, xyz, np.ascontiguousarray(xyz[sample]), o,
+               np.array([512], dtype=np.int32), sqrt=False)
+
+
 # ------------------------------------------------------------------ FPS
 @pytest.mark.parametrize("n,m,b", [(93, 23, 3), (375, 93, 2), (512, 128, 1), (1500, 375, 3), (2048, 512, 2),
                                    (2049, 300, 2), (6000, 1500, 2), (8192, 600, 1), (24000, 6000, 2),
@@ -223,9 +239,30 @@ def test_three_interpolate_forward_backward():
     assert np.allclose(out2.cpu().numpy(), out.detach().cpu().numpy(), rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("B,C,m,n", [(1, 36, 50, 1001), (2, 100, 93, 375), (1, 8, 3, 64), (2, 130, 700, 2048),
+                                     (1, 1024, 93, 372), (3, 6, 40, 100)])
+def test_three_interpolate_odd_shapes(B, C, m, n):
+    """channel counts that are not multiples of 32 / 4, output lengths that do and do not allow the bulk rows,
+    fewer known points than neighbours-per-point variety: TMA-staged and direct kernels agree with the oracle"""
+    from amcontrast3d_b200.layers import three_interpolate
+    rng = np.random.default_rng(C + n)
+    feats = rng.standard_normal((B, C, m)).astype(np.float32)
+    idx = rng.integers(0, m, size=(B, n, 3)).astype(np.int32)
+    w = rng.random((B, n, 3)).astype(np.float32)
+    w /= w.sum(2, keepdims=True)
+    f = _t(feats).requires_grad_(True)
+    out = three_interpolate(f, _t(idx), _t(w))
+    assert np.array_equal(out.detach().cpu().numpy(), oo.three_interpolate(feats, idx, w))
+    go = rng.standard_normal((B, C, n)).astype(np.float32)
+    out.backward(_t(go))
+    assert rel_err(f.grad.cpu().numpy(), oo.three_interpolate_grad(go, idx, w, m)) <= 1e-5
+
+
 # ------------------------------------------------------------------ grouping
 @pytest.mark.parametrize("B,C,N,npoint,ns", [(2, 64, 6000, 1500, 32), (2, 128, 1500, 1500, 32), (3, 3, 6000, 1500, 32),
-                                             (1, 40, 375, 93, 16), (2, 7, 500, 100, 5), (1, 1024, 93, 93, 32)])
+                                             (1, 40, 375, 93, 16), (2, 7, 500, 100, 5), (1, 1024, 93, 93, 32),
+                                             (2, 100, 777, 301, 32), (1, 36, 50, 9, 64), (2, 12, 300, 77, 24),
+                                             (1, 130, 1000, 1, 32), (2, 64, 40, 500, 8)])
 def test_grouping_forward_backward(B, C, N, npoint, ns):
     from amcontrast3d_b200.layers import grouping_operation
     rng = np.random.default_rng(C)
