@@ -173,15 +173,18 @@ __device__ __forceinline__ void bulk_load(uint32_t sdst, const void *gsrc, uint3
         : "memory");
 }
 
-__global__ void __launch_bounds__(256)
+template <int W>
+__global__ void __launch_bounds__(W * 32)
 group_fwd_tma_kernel(int C, int N, int P, int nsample, const float *__restrict__ srcT,
                      const int *__restrict__ idx, float *__restrict__ out) {
+    constexpr int TPW = W * 32;                      // positions per tile
+    constexpr int FWD_LD = TPW + 4;                  // row stride: 4 mod 32 banks -> conflict-free STS.128
     extern __shared__ __align__(128) float tile[];   // [TC][FWD_LD]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.z;
     const int c0 = blockIdx.y * TC;
-    const int p0 = blockIdx.x * TP;
-    const int npos = min(TP, P - p0);                 // multiple of 4 (host checks P % 4 == 0)
+    const int p0 = blockIdx.x * TPW;
+    const int npos = min(TPW, P - p0);                // multiple of 4 (host checks P % 4 == 0)
     const int cc = min(c0 + lane, C - 1);
     const float *src = srcT + (long long)b * N * C + cc;
     const int *ip = idx + (long long)b * P + p0 + warp * 32;
@@ -673,8 +676,18 @@ static int group_common(bool fwd, int b, int c, int n, long long P, const float 
         const int combine = (!no_combine && nsample >= 32 && nsample % 32 == 0) ? nsample : 0;
         if (fwd) {
             launch_transpose<false>(b, c, n, src, workspace, st);  // (B,C,N) -> (B,N,C)
-            if (impl >= 1)
-                group_fwd_tma_kernel<<<grid, 256, TC * FWD_LD * sizeof(float), st>>>(c, n, (int)P, combine, workspace, idx, dst);
+            if (impl >= 1) {
+                static const int fw = getenv("AMC3D_GROUP_FWD_W") ? atoi(getenv("AMC3D_GROUP_FWD_W")) : 4;   // 4 warps x 128 positions measured best
+                if (fw == 4) {
+                    dim3 g4((unsigned)div_up_ll(P, 128), div_up(c, 32), b);
+                    group_fwd_tma_kernel<4><<<g4, 128, TC * (128 + 4) * sizeof(float), st>>>(c, n, (int)P, combine, workspace, idx, dst);
+                } else if (fw == 2) {
+                    dim3 g2((unsigned)div_up_ll(P, 64), div_up(c, 32), b);
+                    group_fwd_tma_kernel<2><<<g2, 64, TC * (64 + 4) * sizeof(float), st>>>(c, n, (int)P, combine, workspace, idx, dst);
+                } else {
+                    group_fwd_tma_kernel<8><<<grid, 256, TC * (256 + 4) * sizeof(float), st>>>(c, n, (int)P, combine, workspace, idx, dst);
+                }
+            }
             else
                 group_fwd_cl_kernel<<<grid, GRP_WARPS * 32, 0, st>>>(c, n, (int)P, workspace, idx, dst);
         } else {
