@@ -62,6 +62,14 @@ SIGNATURES = {
     "amc3d_knnquery_order": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P],
     "amc3d_grouping_forward": [_I, _I, _I, _P, _P, _P, _P],
     "amc3d_grouping_backward": [_I, _I, _I, _P, _P, _P, _P],
+    "amc3d_pointops_ballquery": [_I, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P],
+    "amc3d_pointops_furthestsampling": [_I, _I, _P, _P, _P, _P, _P, _P],
+    "amc3d_pointops_interpolation_forward": [_I, _I, _I, _P, _P, _P, _P, _P],
+    "amc3d_pointops_interpolation_backward": [_I, _I, _I, _P, _P, _P, _P, _P],
+    "amc3d_pointops_subtraction_forward": [_I, _I, _I, _P, _P, _P, _P, _P],
+    "amc3d_pointops_subtraction_backward": [_I, _I, _I, _P, _P, _P, _P, _P],
+    "amc3d_pointops_aggregation_forward": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
+    "amc3d_pointops_aggregation_backward": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "amc3d_stage_labels": [_I, _I, _I, _I, _LL, _P, _P, _P, _P],
     "amc3d_posmask_count": [_I, _I, _I, _P, _P, _P, _P, _P, _P],
     "amc3d_ambiguity": [_I, _I, _I, _P, _P, _P, _P, _P, _I, _F, _F, _P, _P, _P],

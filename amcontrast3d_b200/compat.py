@@ -33,7 +33,12 @@ _T2 = {
     "openpoints.models.layers.upsampling": ("amcontrast3d_b200.layers.upsampling",
                                             ["three_nn", "three_interpolate", "three_interpolation", "ThreeNN",
                                              "ThreeInterpolate"]),
-    "openpoints.cpp.pointops.functions.pointops": ("amcontrast3d_b200.pointops", ["knnquery", "KNNQuery"]),
+    "openpoints.cpp.pointops.functions.pointops": ("amcontrast3d_b200.pointops",
+                                                   ["knnquery", "KNNQuery", "furthestsampling", "FurthestSampling",
+                                                    "ballquery", "BallQuery", "grouping", "Grouping", "querygroup",
+                                                    "queryandgroup", "subtraction", "Subtraction", "aggregation",
+                                                    "Aggregation", "interpolation", "interpolation2",
+                                                    "Interpolation"]),
 }
 _T3 = {
     "openpoints.AMContrast3D.MarginContrast": ("amcontrast3d_b200.AMContrast3D.MarginContrast",

@@ -178,7 +178,7 @@ __device__ __forceinline__ float tree_max(const float (&t)[N]) {
 template <int CS, int PPT, int NW, bool SX>
 __global__ void __launch_bounds__(NW * 32)
 fps_cluster_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, float *__restrict__ temp,
-                   int *__restrict__ idxs, int dbg) {
+                   int *__restrict__ idxs, int ibase, int istride, int dbg) {
     constexpr int NT = NW * 32;
     constexpr int NC = CS * NW;              // candidates per round: one per warp of the cluster
     constexpr int CPL = (NC + 31) / 32;      // candidates per lane
@@ -196,6 +196,7 @@ fps_cluster_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, floa
     xyz += 3ll * batch * n;
     temp += (long long)batch * n;
     idxs += (long long)batch * m;
+    ibase += batch * istride;     // added to every index written (packed layout: global indices)
 
     // Point k of the scene belongs to CTA k % CS, warp (k / CS) % NW, lane (k / (CS*NW)) % 32, slot
     // k / (CS*NW*32): consecutive indices land in different warps.  PointNeXt runs FPS on clouds that
@@ -248,7 +249,7 @@ fps_cluster_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, floa
     cluster_sync_all();
 
     float x1 = __ldg(xyz), y1 = __ldg(xyz + 1), z1 = __ldg(xyz + 2);
-    if (rank == 0 && tid == 0) idxs[0] = 0;
+    if (rank == 0 && tid == 0) idxs[0] = ibase;
 
     // addresses used every round, pinned in registers: without the opaque moves ptxas re-derives the
     // shared window base (S2UR SR_CgaCtaId + ULEA, ~30 cycles of scoreboard wait each) at every use
@@ -413,7 +414,7 @@ fps_cluster_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, floa
             x1 = __shfl_sync(0xffffffffu, sx, gl);
             y1 = __shfl_sync(0xffffffffu, sy, gl);
             z1 = __shfl_sync(0xffffffffu, sz, gl);
-            if (rank == 0 && warp == 0 && lane == gl) idxs[j] = sk;
+            if (rank == 0 && warp == 0 && lane == gl) idxs[j] = sk + ibase;
             // the previous pick, on this thread's points (independent of everything above and below)
             apply_pick(px, py, pz);
             ++q;
@@ -455,7 +456,7 @@ fps_cluster_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, floa
 constexpr int FPS_G_THREADS = 1024;
 __global__ void __launch_bounds__(FPS_G_THREADS)
 fps_global_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, float *__restrict__ temp,
-                  int *__restrict__ idxs) {
+                  int *__restrict__ idxs, int ibase, int istride) {
     __shared__ uint32_t s_v[32], s_tb[32];
     __shared__ int s_k[32];
     __shared__ int s_old;
@@ -463,8 +464,9 @@ fps_global_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, float
     xyz += 3ll * blockIdx.x * n;
     temp += (long long)blockIdx.x * n;
     idxs += (long long)blockIdx.x * m;
+    ibase += blockIdx.x * istride;
     int old = 0;
-    if (tid == 0) idxs[0] = 0;
+    if (tid == 0) idxs[0] = ibase;
     for (int j = 1; j < m; ++j) {
         const float x1 = __ldg(xyz + 3ll * old), y1 = __ldg(xyz + 3ll * old + 1), z1 = __ldg(xyz + 3ll * old + 2);
         uint32_t bv = 0, bt = 0xffffffffu;
@@ -489,14 +491,14 @@ fps_global_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, float
         }
         __syncthreads();
         old = s_old;
-        if (tid == 0) idxs[j] = old;
+        if (tid == 0) idxs[j] = old + ibase;
         __syncthreads();
     }
 }
 
 template <int CS, int PPT, int NW, bool SX = false>
 static cudaError_t launch_cluster(int b, int n, int m, int log2bs, const float *xyz, float *temp, int *idx,
-                                  cudaStream_t st) {
+                                  int ibase, int istride, cudaStream_t st) {
     const size_t smem = (SX ? 3 * sizeof(float) : sizeof(float4)) * PPT * NW * 32;
     auto kern = fps_cluster_kernel<CS, PPT, NW, SX>;
     cudaError_t e;
@@ -521,13 +523,13 @@ static cudaError_t launch_cluster(int b, int n, int m, int log2bs, const float *
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     static const int dbg = getenv("AMC3D_FPS_DEBUG") != nullptr;
-    return cudaLaunchKernelEx(&cfg, kern, n, m, log2bs, xyz, temp, idx, dbg);
+    return cudaLaunchKernelEx(&cfg, kern, n, m, log2bs, xyz, temp, idx, ibase, istride, dbg);
 }
 
-#define FPS_ARGS b, n, m, log2bs, xyz, temp, idx, st
+#define FPS_ARGS b, n, m, log2bs, xyz, temp, idx, ibase, istride, st
 template <int CS, int NW>
 static cudaError_t launch_for_ppt(int ppt, int b, int n, int m, int log2bs, const float *xyz, float *temp, int *idx,
-                                  cudaStream_t st) {
+                                  int ibase, int istride, cudaStream_t st) {
     if (ppt <= 1) return launch_cluster<CS, 1, NW>(FPS_ARGS);
     if (ppt <= 2) return launch_cluster<CS, 2, NW>(FPS_ARGS);
     if (ppt <= 3) return launch_cluster<CS, 3, NW>(FPS_ARGS);
@@ -549,7 +551,7 @@ static cudaError_t launch_for_ppt(int ppt, int b, int n, int m, int log2bs, cons
 
 template <int CS>
 static cudaError_t launch_for_nw(int nw, int b, int n, int m, int log2bs, const float *xyz, float *temp, int *idx,
-                                 cudaStream_t st) {
+                                 int ibase, int istride, cudaStream_t st) {
     const int ppt = div_up(n, CS * nw * 32);
     if (nw == 4) return launch_for_ppt<CS, 4>(ppt, FPS_ARGS);
     if (nw == 8) return launch_for_ppt<CS, 8>(ppt, FPS_ARGS);
@@ -557,7 +559,7 @@ static cudaError_t launch_for_nw(int nw, int b, int n, int m, int log2bs, const 
 }
 
 static cudaError_t launch_for_cs(int cs, int nw, int b, int n, int m, int log2bs, const float *xyz, float *temp,
-                                 int *idx, cudaStream_t st) {
+                                 int *idx, int ibase, int istride, cudaStream_t st) {
     if (cs == 16) return launch_for_nw<16>(nw, FPS_ARGS);
     if (cs == 8) return launch_for_nw<8>(nw, FPS_ARGS);
     if (cs == 4) return launch_for_nw<4>(nw, FPS_ARGS);
@@ -569,20 +571,10 @@ static int env_int(const char *name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
-}  // namespace amc3d
-
-using namespace amc3d;
-
-extern "C" int amc3d_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp,
-                                             int *idx, void *stream) {
-    AMC3D_REQUIRE(b >= 0 && n >= 1 && m >= 0, AMC3D_EINVAL, "furthest_point_sampling: bad sizes b=%d n=%d m=%d", b, n, m);
-    AMC3D_REQUIRE(n <= (1 << 22), AMC3D_ELIMIT, "furthest_point_sampling: n=%d > 4194304", n);
-    if (b == 0 || m <= 0) return 0;  // reference kernel returns immediately for m <= 0
-    cudaStream_t st = as_stream(stream);
-    // reference block size: largest power of two <= n, capped at 1024 (cuda_utils.h:10-14)
-    int log2bs = 0;
-    while ((2 << log2bs) <= n && log2bs < 10) ++log2bs;
-
+// b clouds of n points each, contiguous; log2bs = log2 of the reference's block size (it fixes the tie order);
+// every index written is local index + ibase + cloud * istride.  Returns 0 or a cudaError_t.
+int fps_launch(int b, int n, int m, int log2bs, const float *xyz, float *temp, int *idx, int ibase, int istride,
+               cudaStream_t st) {
     // cluster size and warps per CTA: as much parallelism as pays off (each round costs one
     // exchange regardless); AMC3D_FPS_CS / AMC3D_FPS_NW override the choice for experiments
     static const int env_cs = env_int("AMC3D_FPS_CS", 0), env_nw = env_int("AMC3D_FPS_NW", 0);
@@ -603,7 +595,33 @@ extern "C" int amc3d_furthest_point_sampling(int b, int n, int m, const float *x
     }
     if (e != cudaSuccess) {                    // very large scenes (or clusters unavailable)
         cudaGetLastError();
-        fps_global_kernel<<<b, FPS_G_THREADS, 0, st>>>(n, m, log2bs, xyz, temp, idx);
+        fps_global_kernel<<<b, FPS_G_THREADS, 0, st>>>(n, m, log2bs, xyz, temp, idx, ibase, istride);
     }
+    return 0;
+}
+
+// `count` consecutive segments of the packed layout, all of n points and m samples (pointops_packed.cu)
+int fps_segments(int count, int n, int m, int log2bs, const float *xyz, float *temp, int *idx, int idx_base,
+                 cudaStream_t st) {
+    if (n > (1 << 22)) {
+        set_error("pointops_furthestsampling: segment of %d points > 4194304", n);
+        return AMC3D_ELIMIT;
+    }
+    return fps_launch(count, n, m, log2bs, xyz, temp, idx, idx_base, n, st);
+}
+
+}  // namespace amc3d
+
+using namespace amc3d;
+
+extern "C" int amc3d_furthest_point_sampling(int b, int n, int m, const float *xyz, float *temp,
+                                             int *idx, void *stream) {
+    AMC3D_REQUIRE(b >= 0 && n >= 1 && m >= 0, AMC3D_EINVAL, "furthest_point_sampling: bad sizes b=%d n=%d m=%d", b, n, m);
+    AMC3D_REQUIRE(n <= (1 << 22), AMC3D_ELIMIT, "furthest_point_sampling: n=%d > 4194304", n);
+    if (b == 0 || m <= 0) return 0;  // reference kernel returns immediately for m <= 0
+    // reference block size: largest power of two <= n, capped at 1024 (cuda_utils.h:10-14)
+    int log2bs = 0;
+    while ((2 << log2bs) <= n && log2bs < 10) ++log2bs;
+    fps_launch(b, n, m, log2bs, xyz, temp, idx, 0, 0, as_stream(stream));
     return check_launch("furthest_point_sampling");
 }

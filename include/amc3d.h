@@ -168,6 +168,52 @@ int amc3d_grouping_forward(int m, int nsample, int c, const float *input, const 
 int amc3d_grouping_backward(int m, int nsample, int c, const float *grad_output,
                             const int *idx, float *grad_input, void *stream);
 
+/* The remaining pointops exports (no caller in AMContrast3D; they serve Point-Transformer style models
+ * of OpenPoints and complete the `pointops_cuda` module surface, pointops_api.cpp:13-25). */
+
+/* Ball query inside each offset segment: the first nsample support points (index order) with
+ * d2 < radius*radius, global indices; slots past the hit count repeat the first hit; rows without a hit
+ * are left as the caller filled them (zeros).  Sizes and offsets as for amc3d_knnquery.
+ * ref: pointops/src/ballquery/ballquery_cuda.cpp:35, ballquery_cuda_kernel.cu:27-76 */
+int amc3d_pointops_ballquery(int n, int m, int nseg, float radius, int nsample, const float *xyz,
+                             const float *new_xyz, const int *offset, const int *new_offset, int *idx,
+                             void *stream);
+/* Furthest point sampling inside each segment: idx[new_offset[s-1] ..) = new_offset[s]-new_offset[s-1]
+ * picks of segment s as GLOBAL indices, starting with the segment's first point.  h_offset and
+ * h_new_offset are HOST copies of the cumulative ends (the reference's Python wrapper reads them on the
+ * host too, pointops.py:20-23); n_max = the largest segment (it fixes the reference's block size and so
+ * the order in which equal distances resolve); tmp (n) f32 = 1e10 on entry, clobbered.
+ * ref: pointops/src/sampling/sampling_cuda.cpp furthestsampling_cuda, sampling_cuda_kernel.cu:13-133 */
+int amc3d_pointops_furthestsampling(int nseg, int n_max, const float *xyz, const int *h_offset,
+                                    const int *h_new_offset, float *tmp, int *idx, void *stream);
+/* output[i,:] += sum_j input[idx[i,j],:] * weight[i,j]  (an FMA chain in j order from the caller's
+ * output).  input (m,c), idx / weight (n,k), output (n,c).
+ * ref: pointops/src/interpolation/interpolation_cuda_kernel.cu:5-18 / :20-32 */
+int amc3d_pointops_interpolation_forward(int n, int c, int k, const float *input, const int *idx,
+                                         const float *weight, float *output, void *stream);
+/* grad_input[idx[i,j],:] += grad_output[i,:] * weight[i,j]; grad_input (m,c) pre-zeroed. */
+int amc3d_pointops_interpolation_backward(int n, int c, int k, const float *grad_output, const int *idx,
+                                          const float *weight, float *grad_input, void *stream);
+/* output[i,s,:] = input1[i,:] - input2[idx[i,s],:].  input1, input2 (n,c), idx (n,nsample).
+ * ref: pointops/src/subtraction/subtraction_cuda_kernel.cu:5-16 / :18-31 */
+int amc3d_pointops_subtraction_forward(int n, int nsample, int c, const float *input1, const float *input2,
+                                       const int *idx, float *output, void *stream);
+/* grad_input1[i,:] += g, grad_input2[idx[i,s],:] -= g with g = grad_output[i,s,:]; both pre-zeroed. */
+int amc3d_pointops_subtraction_backward(int n, int nsample, int c, const int *idx, const float *grad_output,
+                                        float *grad_input1, float *grad_input2, void *stream);
+/* output[i,ch] += sum_s (input[idx[i,s],ch] + position[i,s,ch]) * weight[i,s,ch % w_c]  (FMA chain in s
+ * order).  input (n,c), position (n,nsample,c), weight (n,nsample,w_c), idx (n,nsample), output (n,c).
+ * ref: pointops/src/aggregation/aggregation_cuda_kernel.cu:5-21 */
+int amc3d_pointops_aggregation_forward(int n, int nsample, int c, int w_c, const float *input,
+                                       const float *position, const float *weight, const int *idx,
+                                       float *output, void *stream);
+/* grad_input (n,c) and grad_weight (n,nsample,w_c) accumulate (pre-zeroed); grad_position (n,nsample,c)
+ * is written.  ref: aggregation_cuda_kernel.cu:24-41 */
+int amc3d_pointops_aggregation_backward(int n, int nsample, int c, int w_c, const float *input,
+                                        const float *position, const float *weight, const int *idx,
+                                        const float *grad_output, float *grad_input, float *grad_position,
+                                        float *grad_weight, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * adaptive-margin contrastive loss (one decoder stage)
  * ref: openpoints/AMContrast3D/MarginContrast.py:220-259, AEF/ambiguity.py:11-93,

@@ -175,3 +175,95 @@ def knnquery(nsample, xyz, new_xyz, offset, new_offset, lex=False, threads=None)
     _parallel(m, lambda lo, hi: fn(lo, hi, nsample, int(offset.shape[0]), _p(xyz), _p(new_xyz),
                                    _p(offset), _p(new_offset), _p(idx), _p(dist2)), threads)
     return idx, dist2
+
+
+# ---- the remaining pointops kernels (packed layout) --------------------------------------------------
+
+def pop_furthestsampling(xyz, offset, new_offset):
+    """sampling_cuda_kernel.cu:13-133 with the wrapper's n_max / tmp=1e10 (pointops.py:18-26)
+    -> idx (new_offset[-1]) i32, global indices."""
+    xyz, offset, new_offset = _f32(xyz), _i32(offset), _i32(new_offset)
+    sizes = np.diff(np.concatenate([[0], offset]))
+    n_max = int(sizes.max()) if sizes.size else 0
+    idx = np.zeros((int(new_offset[-1]) if new_offset.size else 0,), dtype=np.int32)
+    tmp = np.full((xyz.shape[0],), 1e10, dtype=np.float32)
+    _load().oracle_pop_fps(int(offset.shape[0]), n_max, _p(xyz), _p(offset), _p(new_offset), _p(tmp), _p(idx))
+    return idx
+
+
+def pop_ballquery(radius, nsample, xyz, new_xyz, offset, new_offset, threads=None):
+    """ballquery_cuda_kernel.cu:27-76 -> idx (m,nsample) i32 (rows without a hit stay zero)"""
+    xyz = _f32(xyz)
+    new_xyz = xyz if new_xyz is None else _f32(new_xyz)
+    offset, new_offset = _i32(offset), _i32(new_offset)
+    m = new_xyz.shape[0]
+    idx = np.zeros((m, int(nsample)), dtype=np.int32)
+    lib = _load()
+    _parallel(m, lambda lo, hi: lib.oracle_pop_ballquery_range(lo, hi, ctypes.c_float(radius), int(nsample), _p(xyz),
+                                                               _p(new_xyz), _p(offset), _p(new_offset), _p(idx)),
+              threads)
+    return idx
+
+
+def pop_interpolation_fwd(input, idx, weight, output=None):
+    """interpolation_cuda_kernel.cu:5-18 -> (n,c); accumulates into `output` when given"""
+    input, idx, weight = _f32(input), _i32(idx), _f32(weight)
+    n, k = idx.shape
+    c = input.shape[1]
+    out = np.zeros((n, c), dtype=np.float32) if output is None else _f32(output).copy()
+    _load().oracle_pop_interpolation_fwd(n, c, k, _p(input), _p(idx), _p(weight), _p(out))
+    return out
+
+
+def pop_interpolation_bwd(grad_output, idx, weight, m):
+    """interpolation_cuda_kernel.cu:20-32 -> grad_input (m,c)"""
+    grad_output, idx, weight = _f32(grad_output), _i32(idx), _f32(weight)
+    n, k = idx.shape
+    c = grad_output.shape[1]
+    g = np.zeros((int(m), c), dtype=np.float32)
+    _load().oracle_pop_interpolation_bwd(n, c, k, _p(grad_output), _p(idx), _p(weight), _p(g))
+    return g
+
+
+def pop_subtraction_fwd(input1, input2, idx):
+    """subtraction_cuda_kernel.cu:5-16 -> (n,nsample,c)"""
+    input1, input2, idx = _f32(input1), _f32(input2), _i32(idx)
+    n, c = input1.shape
+    nsample = idx.shape[1]
+    out = np.zeros((n, nsample, c), dtype=np.float32)
+    _load().oracle_pop_subtraction_fwd(n, nsample, c, _p(input1), _p(input2), _p(idx), _p(out))
+    return out
+
+
+def pop_subtraction_bwd(idx, grad_output, n2=None):
+    """subtraction_cuda_kernel.cu:18-31 -> (grad_input1 (n,c), grad_input2 (n,c))"""
+    idx, grad_output = _i32(idx), _f32(grad_output)
+    n, nsample, c = grad_output.shape
+    g1 = np.zeros((n, c), dtype=np.float32)
+    g2 = np.zeros((n if n2 is None else int(n2), c), dtype=np.float32)
+    _load().oracle_pop_subtraction_bwd(n, nsample, c, _p(idx), _p(grad_output), _p(g1), _p(g2))
+    return g1, g2
+
+
+def pop_aggregation_fwd(input, position, weight, idx):
+    """aggregation_cuda_kernel.cu:5-21 -> (n,c)"""
+    input, position, weight, idx = _f32(input), _f32(position), _f32(weight), _i32(idx)
+    n, nsample, c = position.shape
+    w_c = weight.shape[-1]
+    out = np.zeros((n, c), dtype=np.float32)
+    _load().oracle_pop_aggregation_fwd(n, nsample, c, w_c, _p(input), _p(position), _p(weight), _p(idx), _p(out))
+    return out
+
+
+def pop_aggregation_bwd(input, position, weight, idx, grad_output):
+    """aggregation_cuda_kernel.cu:24-41 -> (grad_input, grad_position, grad_weight)"""
+    input, position, weight, idx = _f32(input), _f32(position), _f32(weight), _i32(idx)
+    grad_output = _f32(grad_output)
+    n, nsample, c = position.shape
+    w_c = weight.shape[-1]
+    gi = np.zeros_like(input)
+    gp = np.zeros_like(position)
+    gw = np.zeros_like(weight)
+    _load().oracle_pop_aggregation_bwd(n, nsample, c, w_c, _p(input), _p(position), _p(weight), _p(idx),
+                                       _p(grad_output), _p(gi), _p(gp), _p(gw))
+    return gi, gp, gw

@@ -16,8 +16,10 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "_ref", "libref_kernels.so")
+LIB_POP = os.path.join(HERE, "_ref", "libref_pointops.so")     # the remaining pointops kernels
 REF_ROOT = "/root/reference"
 _lib = None
+_lib_pop = None
 
 
 def available() -> bool:
@@ -26,7 +28,7 @@ def available() -> bool:
 
 def build() -> str | None:
     """Build from /root/reference when it exists (the container); the GPU box uses the prebuilt file."""
-    if os.path.isdir(REF_ROOT) and not os.path.exists(LIB):
+    if os.path.isdir(REF_ROOT) and not (os.path.exists(LIB) and os.path.exists(LIB_POP)):
         subprocess.run(["make", "-C", HERE, "-j6", "ref"], check=True, capture_output=True)
     return LIB if os.path.exists(LIB) else None
 
@@ -128,3 +130,93 @@ def knnquery(nsample, xyz, new_xyz, offset, new_offset):
     _load().ref_knnquery(m, int(nsample), _p(xyz), _p(new_xyz), _p(offset), _p(new_offset), _p(idx), _p(dist2))
     sync()
     return idx, dist2
+
+
+# ---- the remaining pointops kernels (oracle/_ref/libref_pointops.so) -----------------------------------
+
+def pointops_available() -> bool:
+    return os.path.exists(LIB_POP)
+
+
+def _pop():
+    global _lib_pop
+    if _lib_pop is None:
+        if not pointops_available():
+            raise RuntimeError("oracle/_ref/libref_pointops.so is missing (make -C oracle ref)")
+        _lib_pop = ctypes.CDLL(LIB_POP)
+    return _lib_pop
+
+
+def _pop_run(name, *args):
+    torch.cuda.synchronize()
+    getattr(_pop(), name)(*args)
+    rc = _pop().ref_pop_sync()
+    if rc != 0:
+        raise RuntimeError(f"reference kernel {name} failed: cudaError {rc}")
+
+
+def pop_furthestsampling(xyz, offset, new_offset):
+    """pointops.py:10-28: n_max over the segments, tmp = 1e10"""
+    h = offset.cpu().long()
+    n_max = int(torch.diff(h, prepend=h.new_zeros(1)).max())
+    idx = torch.zeros((int(new_offset[-1]),), dtype=torch.int32, device=xyz.device)
+    tmp = torch.full((xyz.shape[0],), 1e10, dtype=torch.float32, device=xyz.device)
+    _pop_run("ref_pop_fps", int(offset.shape[0]), n_max, _p(xyz), _p(offset), _p(new_offset), _p(tmp), _p(idx))
+    return idx, tmp
+
+
+def pop_ballquery(radius, nsample, xyz, new_xyz, offset, new_offset):
+    m = new_xyz.shape[0]
+    idx = torch.zeros((m, nsample), dtype=torch.int32, device=xyz.device)
+    _pop_run("ref_pop_ballquery", m, ctypes.c_float(radius), int(nsample), _p(xyz), _p(new_xyz), _p(offset),
+             _p(new_offset), _p(idx))
+    return idx
+
+
+def pop_interpolation_fwd(input, idx, weight):
+    n, k = idx.shape
+    c = input.shape[1]
+    out = torch.zeros((n, c), dtype=torch.float32, device=input.device)
+    _pop_run("ref_pop_interpolation_fwd", n, c, k, _p(input), _p(idx), _p(weight), _p(out))
+    return out
+
+
+def pop_interpolation_bwd(grad_output, idx, weight, m):
+    n, k = idx.shape
+    c = grad_output.shape[1]
+    g = torch.zeros((int(m), c), dtype=torch.float32, device=grad_output.device)
+    _pop_run("ref_pop_interpolation_bwd", n, c, k, _p(grad_output), _p(idx), _p(weight), _p(g))
+    return g
+
+
+def pop_subtraction_fwd(input1, input2, idx):
+    n, c = input1.shape
+    ns = idx.shape[1]
+    out = torch.zeros((n, ns, c), dtype=torch.float32, device=input1.device)
+    _pop_run("ref_pop_subtraction_fwd", n, ns, c, _p(input1), _p(input2), _p(idx), _p(out))
+    return out
+
+
+def pop_subtraction_bwd(idx, grad_output):
+    n, ns, c = grad_output.shape
+    g1 = torch.zeros((n, c), dtype=torch.float32, device=grad_output.device)
+    g2 = torch.zeros((n, c), dtype=torch.float32, device=grad_output.device)
+    _pop_run("ref_pop_subtraction_bwd", n, ns, c, _p(idx), _p(grad_output), _p(g1), _p(g2))
+    return g1, g2
+
+
+def pop_aggregation_fwd(input, position, weight, idx):
+    n, ns, c = position.shape
+    w_c = weight.shape[-1]
+    out = torch.zeros((n, c), dtype=torch.float32, device=input.device)
+    _pop_run("ref_pop_aggregation_fwd", n, ns, c, w_c, _p(input), _p(position), _p(weight), _p(idx), _p(out))
+    return out
+
+
+def pop_aggregation_bwd(input, position, weight, idx, grad_output):
+    n, ns, c = position.shape
+    w_c = weight.shape[-1]
+    gi, gp, gw = torch.zeros_like(input), torch.zeros_like(position), torch.zeros_like(weight)
+    _pop_run("ref_pop_aggregation_bwd", n, ns, c, w_c, _p(input), _p(position), _p(weight), _p(idx), _p(grad_output),
+             _p(gi), _p(gp), _p(gw))
+    return gi, gp, gw
