@@ -2,4 +2,4 @@
 names, call signatures and return values as the reference, running on the sm_100a kernels."""
 from .MarginContrast import AmbiguityHead, ContrastHead
 from .MaskedRefine import RefinementMethod
-from .metrics import posmask_searching
+from .metrics import ambiguity_metrics, ambiguity_summary, posmask_searching
