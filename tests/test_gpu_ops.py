@@ -217,6 +217,33 @@ def test_three_nn(n, m):
     assert np.array_equal(dist.cpu().numpy(), np.sqrt(rd2))
 
 
+def test_three_nn_dense_queries_thread_per_query_path():
+    """>= 128k query slots, at least twice as many queries as known points, k <= 4: the thread-per-query search
+    (knn_grid.cu 4b).  Lattice points put exact distance ties on most rows."""
+    from amcontrast3d_b200.layers import three_nn
+    xyz, _ = scenes.batch_of_scenes(6, 22000, "surface", first_scene=16)
+    known = np.ascontiguousarray(xyz[:, ::11])                               # 2000 known points per cloud
+    rd2, ri = oo.three_nn(xyz, known)
+    dist, idx = three_nn(_t(xyz), _t(known))
+    assert np.array_equal(idx.cpu().numpy(), ri) and np.array_equal(dist.cpu().numpy(), np.sqrt(rd2))
+    rng = np.random.default_rng(4)
+    lat_u = rng.integers(0, 24, size=(6, 22000, 3)).astype(np.float32) * 0.125
+    lat_k = rng.integers(0, 24, size=(6, 1800, 3)).astype(np.float32) * 0.125
+    rd2, ri = oo.three_nn(lat_u, lat_k)
+    dist, idx = three_nn(_t(lat_u), _t(lat_k))
+    assert np.array_equal(idx.cpu().numpy(), ri) and np.array_equal(dist.cpu().numpy(), np.sqrt(rd2))
+
+
+@pytest.mark.parametrize("k", [1, 2, 4])
+def test_knn_dense_queries_thread_per_query_path(k):
+    from amcontrast3d_b200 import _amloss
+    xyz, _ = scenes.surface_scene(140000, seed=12)
+    sup = np.ascontiguousarray(xyz[::14])                                    # 10 000 support points, one segment
+    o, qo = np.array([sup.shape[0]], np.int32), np.array([xyz.shape[0]], np.int32)
+    idx, d2 = _amloss.knn_raw(k, _t(sup), _t(xyz), _t(o), _t(qo))
+    _check_knn(idx.cpu().numpy(), d2.cpu().numpy(), k, sup, xyz, o, qo, sqrt=False)
+
+
 def test_three_interpolate_forward_backward():
     from amcontrast3d_b200.layers import three_interpolate, three_interpolation
     rng = np.random.default_rng(2)
