@@ -332,25 +332,27 @@ struct WarpList {
     }
 };
 
-// An upper bound T of the k-th smallest of the 4 x 32 distances held by the warp, tight to 2^-7
+// An upper bound T of the k-th smallest of the NV x 32 distances held by the warp, tight to 2^-7
 // relative: radix select on the bit pattern (non-negative floats order like their bits) over bits
 // 30..17, two bits per step — the counts for the three candidate prefixes travel in one packed
-// REDUX.SUM (each count <= 128 fits a byte) — and the 17 low bits rounded up.  #{d <= T} >= k always;
-// the handful of extra candidates a looser T lets through fall off the end of the sorted list.
-__device__ __forceinline__ float warp_kth_bound_of_128(const float (&dd)[GR], int k) {
-    uint32_t v[GR];
+// REDUX.SUM (each count <= 32 NV <= 1023 fits ten bits) — and the 17 low bits rounded up.  #{d <= T} >= k
+// always; the handful of extra candidates a looser T lets through fall off the end of the sorted list.
+template <int NV>
+__device__ __forceinline__ float warp_kth_bound(const float (&dd)[NV], int k) {
+    static_assert(NV * 32 < 1024, "packed counters are ten bits wide");
+    uint32_t v[NV];
 #pragma unroll
-    for (int r = 0; r < GR; ++r) v[r] = __float_as_uint(dd[r]);
+    for (int r = 0; r < NV; ++r) v[r] = __float_as_uint(dd[r]);
     uint32_t T = 0;
 #pragma unroll
     for (int b = 29; b >= 17; b -= 2) {
         const uint32_t t1 = T | (1u << b), t2 = T | (2u << b), t3 = T | (3u << b);
         uint32_t c = 0;
 #pragma unroll
-        for (int r = 0; r < GR; ++r)
-            c += (v[r] < t1 ? 1u : 0u) + (v[r] < t2 ? 0x100u : 0u) + (v[r] < t3 ? 0x10000u : 0u);
+        for (int r = 0; r < NV; ++r)
+            c += (v[r] < t1 ? 1u : 0u) + (v[r] < t2 ? 0x400u : 0u) + (v[r] < t3 ? 0x100000u : 0u);
         c = __reduce_add_sync(0xffffffffu, c);
-        const int c1 = c & 0xff, c2 = (c >> 8) & 0xff, c3 = c >> 16;
+        const int c1 = c & 0x3ff, c2 = (c >> 10) & 0x3ff, c3 = c >> 20;
         // fewer than k values below a prefix: the k-th is >= that prefix
         T = c3 < k ? t3 : (c2 < k ? t2 : (c1 < k ? t1 : T));
     }
@@ -381,7 +383,7 @@ knn_wq_kernel(Geom gs, int m, int mpad, int nsample, int self, int qpw, const fl
     for (int j = 0; j < qpw; ++j) {
         const int q = wq0 + j;
         if (q >= gs.nb * mpad) return;                        // warp-uniform
-        const int b = q / mpad;
+        const int b = gs.nb == 1 ? 0 : q / mpad;
         if (q - b * mpad >= m) continue;                      // padding slot of the query layout
         const float4 me = __ldg(sq + q);
         // the visiting order (spatially coherent) for callers that want to process the queries the same way
@@ -393,41 +395,39 @@ knn_wq_kernel(Geom gs, int m, int mpad, int nsample, int self, int qpw, const fl
         int ti = 0x7fffffff;
         const int tb0 = b * gs.ntb;                           // first tile of the query's cloud
 
-        // evaluate the 128 points of global tile t against this query; first=true seeds the list
-        auto process_tile = [&](int t, bool first) {
-            float dd[GR];
-            int oi[GR];
-#pragma unroll
-            for (int r = 0; r < GR; ++r) {
-                const int l = (t - tb0) * GT + r * 32 + lane;  // position within the cloud
-                if (l < n) {
-                    const float4 p = __ldg(sp + (long long)t * GT + r * 32 + lane);
-                    dd[r] = dist2_ref(qx - p.x, qy - p.y, qz - p.z);
-                    oi[r] = __float_as_int(p.w);
-                } else {
-                    dd[r] = INFINITY;
-                    oi[r] = 0x7fffffff;
-                }
-            }
-            if (first) {
-                // bulk seed: only the ~k nearest of the first tile go through the insertion, and
-                // without the per-insert threshold refresh (an entry beyond the k-th falls off the list)
-                td = fminf(warp_kth_bound_of_128(dd, min(nsample, GT)), KG_INIT);
+        // distances of this lane's GR points of global tile t (+inf past the end of the cloud or for a tile
+        // outside it)
+        auto eval_tile = [&](int t, float *dd, int *oi) {
+            const float4 *tp = sp + (long long)t * GT + lane;
+            const int left = (t >= tb0 && t < tb0 + gs.ntb) ? n - (t - tb0) * GT : 0;
+            if (left >= GT) {                                  // a whole tile (all but the last of a cloud)
 #pragma unroll
                 for (int r = 0; r < GR; ++r) {
-                    uint32_t mask = __ballot_sync(0xffffffffu, dd[r] <= td);
-                    while (mask) {
-                        const int bl = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        best.insert(__shfl_sync(0xffffffffu, dd[r], bl), __shfl_sync(0xffffffffu, oi[r], bl), lane);
+                    const float4 p = __ldg(tp + r * 32);
+                    dd[r] = dist2_ref(qx - p.x, qy - p.y, qz - p.z);
+                    oi[r] = __float_as_int(p.w);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < GR; ++r) {
+                    dd[r] = INFINITY;
+                    oi[r] = 0x7fffffff;
+                    if (r * 32 + lane < left) {
+                        const float4 p = __ldg(tp + r * 32);
+                        dd[r] = dist2_ref(qx - p.x, qy - p.y, qz - p.z);
+                        oi[r] = __float_as_int(p.w);
                     }
                 }
-                best.threshold(td, ti);
-                return;
             }
+        };
+        // evaluate the 128 points of global tile t against this query
+        auto process_tile = [&](int t) {
+            float dd[GR];
+            int oi[GR];
+            eval_tile(t, dd, oi);
 #pragma unroll
             for (int r = 0; r < GR; ++r) {
-                bool cand = dd[r] <= td && lex_lt(dd[r], oi[r], td, ti);
+                bool cand = lex_lt(dd[r], oi[r], td, ti);
                 uint32_t mask = __ballot_sync(0xffffffffu, cand);
                 while (mask) {
                     const int bl = __ffs(mask) - 1;
@@ -445,7 +445,13 @@ knn_wq_kernel(Geom gs, int m, int mpad, int nsample, int self, int qpw, const fl
             }
         };
 
-        // ---- the tile at the query's own position and its two neighbours first -------------
+        // ---- seed: the tile at the query's own position; then its two neighbours along the curve ----------
+        // A warp radix-select over the own tile's 128 distances gives its k-th smallest up front, so only the
+        // ~k nearest go through the insertion, and without the per-insert threshold refresh (an entry beyond
+        // the k-th falls off the list).  The neighbours follow unconditionally: skipping them costs 2.4x the
+        // search time (a query near the edge of its tile would start the box tests with a bound that lets
+        // most of the surrounding tiles through); selecting over all three tiles at once costs 10 % (the
+        // select over 12 values per lane is dearer than the insertions it saves).
         int t0;
         if (self) t0 = q / GT;
         else
@@ -453,9 +459,24 @@ knn_wq_kernel(Geom gs, int m, int mpad, int nsample, int self, int qpw, const fl
                   b * (gs.npad - n)) / GT;
         t0 = min(max(t0, tb0), tb0 + gs.ntb - 1);
         const int r_lo = max(t0 - 1, tb0), r_hi = min(t0 + 1, tb0 + gs.ntb - 1);
-        process_tile(t0, true);
+        {
+            float dd[GR];
+            int oi[GR];
+            eval_tile(t0, dd, oi);
+            td = fminf(warp_kth_bound<GR>(dd, min(nsample, GT)), KG_INIT);
+#pragma unroll
+            for (int r = 0; r < GR; ++r) {
+                uint32_t mask = __ballot_sync(0xffffffffu, dd[r] <= td);
+                while (mask) {
+                    const int bl = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    best.insert(__shfl_sync(0xffffffffu, dd[r], bl), __shfl_sync(0xffffffffu, oi[r], bl), lane);
+                }
+            }
+            best.threshold(td, ti);
+        }
         for (int t = r_lo; t <= r_hi; ++t)
-            if (t != t0) process_tile(t, false);
+            if (t != t0) process_tile(t);
 
         // ---- everything else through two levels of boxes -----------------------------------
         for (int g0 = 0; g0 < gs.ngb; g0 += 32) {
@@ -477,7 +498,7 @@ knn_wq_kernel(Geom gs, int m, int mpad, int nsample, int self, int qpw, const fl
                     tmask &= tmask - 1;
                     const float lbt = __shfl_sync(0xffffffffu, lb, tbit);
                     if (lbt * KG_SAFE > td) continue;              // threshold tightened meanwhile
-                    process_tile(tb0 + (g0 + gb) * TG + tbit, false);
+                    process_tile(tb0 + (g0 + gb) * TG + tbit);
                 }
             }
         }
@@ -696,7 +717,7 @@ ball_wq_kernel(Geom gs, int m, int mpad, float radius, int nsample, int self, in
     for (int j = 0; j < qpw; ++j) {
         const int q = wq0 + j;
         if (q >= gs.nb * mpad) return;                        // warp-uniform
-        const int b = q / mpad;
+        const int b = gs.nb == 1 ? 0 : q / mpad;
         if (q - b * mpad >= m) continue;
         const float4 me = __ldg(sq + q);
         const float qx = me.x, qy = me.y, qz = me.z;
@@ -706,12 +727,12 @@ ball_wq_kernel(Geom gs, int m, int mpad, float radius, int nsample, int self, in
         const int tb0 = b * gs.ntb;
 
         auto process_tile = [&](int t) {
+            const int left = n - (t - tb0) * GT;               // >= GT for all but the last tile of a cloud
 #pragma unroll
             for (int r = 0; r < GR; ++r) {
-                const int l = (t - tb0) * GT + r * 32 + lane;
                 bool cand = false;
                 int oi = 0x7fffffff;
-                if (l < n) {
+                if (left >= GT || r * 32 + lane < left) {
                     const float4 p = __ldg(sp + (long long)t * GT + r * 32 + lane);
                     // operand order of the reference: new_xyz - xyz (ball_query_gpu.cu:38-40)
                     const float d = dist2_ref(qx - p.x, qy - p.y, qz - p.z);
