@@ -115,8 +115,15 @@ class BallQuery(Function):
 ballquery = BallQuery.apply
 
 
-def _relative_groups(xyz, new_xyz, flat_idx, m, nsample):
-    rel = xyz[flat_idx, :].view(m, nsample, 3)
+def _gather_rows(table, idx):
+    """table (n,c), idx (m,nsample) i32 -> (m,nsample,c) by torch indexing (differentiable w.r.t. table)"""
+    m, nsample = idx.shape
+    return table[idx.reshape(-1).long(), :].view(m, nsample, table.shape[1])
+
+
+def _offsets_from(xyz, new_xyz, idx):
+    """neighbour coordinates relative to their query, (m,nsample,3)"""
+    rel = _gather_rows(xyz, idx)
     rel -= new_xyz.unsqueeze(1)
     return rel
 
@@ -124,7 +131,11 @@ def _relative_groups(xyz, new_xyz, flat_idx, m, nsample):
 def querygroup(nsample, xyz, new_xyz, feat, offset, new_offset, radius=None, query_method='knn',
                normalize_dp=False, idx=None):
     """Neighbour search (kNN or ball) followed by grouping of coordinates (relative to the query) and
-    features -> (grouped_xyz (m,nsample,3), grouped_feat (m,nsample,c) or None)  (pointops.py:111-158)."""
+    features -> (grouped_xyz (m,nsample,3), grouped_feat (m,nsample,c) or None)  (pointops.py:111-158).
+
+    query_method 'knn' / 'knnquery' selects the kNN, anything else the ball query of `radius`.  With
+    normalize_dp the offsets are divided by the largest offset norm of their group (+1e-8) for 'knn', by
+    `radius` otherwise — including for the spelling 'knnquery', as in the reference."""
     assert xyz.is_contiguous() and new_xyz.is_contiguous() and feat.is_contiguous()
     if new_xyz is None:
         new_xyz = xyz
@@ -132,37 +143,34 @@ def querygroup(nsample, xyz, new_xyz, feat, offset, new_offset, radius=None, que
         # the reference only forms the groups when it ran the search itself; with a caller-provided idx
         # its locals are unbound (pointops.py:157) — raise the same way, with a message
         raise UnboundLocalError("querygroup: idx given by the caller — the reference forms no groups in this case")
-    if nsample is None:
-        return xyz.transpose(1, 2).unsqueeze(2), (feat.unsqueeze(2) if feat is not None else None)
-    if query_method in ('knn', 'knnquery'):
-        idx, _ = knnquery(nsample, xyz, new_xyz, offset, new_offset)
-    else:
-        idx = ballquery(radius, nsample, xyz, new_xyz, offset, new_offset)
-    flat = idx.flatten().long()
-    m = new_xyz.shape[0]
-    grouped_xyz = _relative_groups(xyz, new_xyz, flat, m, nsample)
+    if nsample is None:                                         # "group everything": no search at all
+        return xyz.transpose(1, 2).unsqueeze(2), (None if feat is None else feat.unsqueeze(2))
+    use_knn = query_method in ('knn', 'knnquery')
+    idx = (knnquery(nsample, xyz, new_xyz, offset, new_offset)[0] if use_knn
+           else ballquery(radius, nsample, xyz, new_xyz, offset, new_offset))
+    grouped_xyz = _offsets_from(xyz, new_xyz, idx)
     if normalize_dp:
         if query_method == 'knn':
-            scale = grouped_xyz.norm(dim=-1, p=2, keepdim=True).max(dim=-1, keepdim=True)[0] + 1.0e-8
+            reach = grouped_xyz.norm(dim=-1, p=2, keepdim=True).max(dim=-1, keepdim=True)[0] + 1.0e-8
+            grouped_xyz /= reach
         else:
-            scale = radius
-        grouped_xyz /= scale
-    grouped_feat = feat[flat, :].view(m, nsample, feat.shape[1]) if feat is not None else None
-    return grouped_xyz, grouped_feat
+            grouped_xyz /= radius
+    return grouped_xyz, (None if feat is None else _gather_rows(feat, idx))
 
 
 def queryandgroup(nsample, xyz, new_xyz, feat, idx, offset, new_offset, use_xyz=True):
-    """kNN groups of [relative xyz | features] -> (m,nsample,3+c), or features only (pointops.py:161-184)"""
+    """kNN groups of [relative xyz | features] -> (m,nsample,3+c), or features only (pointops.py:161-184).
+    `idx` (m,nsample) skips the search."""
     assert xyz.is_contiguous() and new_xyz.is_contiguous() and feat.is_contiguous()
     if new_xyz is None:
         new_xyz = xyz
     if idx is None:
-        idx, _ = knnquery(nsample, xyz, new_xyz, offset, new_offset)
-    flat = idx.view(-1).long()
-    m = new_xyz.shape[0]
-    grouped_xyz = _relative_groups(xyz, new_xyz, flat, m, nsample)
-    grouped_feat = feat[flat, :].view(m, nsample, feat.shape[1])
-    return torch.cat((grouped_xyz, grouped_feat), -1) if use_xyz else grouped_feat
+        idx = knnquery(nsample, xyz, new_xyz, offset, new_offset)[0]
+    idx = idx.view(new_xyz.shape[0], nsample)
+    grouped_feat = _gather_rows(feat, idx)
+    if not use_xyz:
+        return grouped_feat
+    return torch.cat((_offsets_from(xyz, new_xyz, idx), grouped_feat), -1)
 
 
 class Subtraction(Function):
@@ -221,6 +229,8 @@ aggregation = Aggregation.apply
 
 
 def _idw(xyz, new_xyz, offset, new_offset, k):
+    """k nearest known points of every new point and their normalised inverse-distance weights
+    w = (1/(d+1e-8)) / sum_k (1/(d+1e-8))  -> (idx (n,k) i32, w (n,k) f32)"""
     idx, dist = knnquery(k, xyz, new_xyz, offset, new_offset)
     inv = 1.0 / (dist + 1e-8)
     return idx, inv / torch.sum(inv, dim=1, keepdim=True)
@@ -228,13 +238,14 @@ def _idw(xyz, new_xyz, offset, new_offset, k):
 
 def interpolation(xyz, new_xyz, feat, offset, new_offset, k=3):
     """Inverse-distance interpolation of feat (m,c) at xyz (m,3) onto new_xyz (n,3), composed from torch
-    ops so that autograd differentiates it (pointops.py:259-274)."""
+    ops so that autograd differentiates it (pointops.py:259-274): one weighted row gather per neighbour
+    rank, accumulated in rank order."""
     assert xyz.is_contiguous() and new_xyz.is_contiguous() and feat.is_contiguous()
     idx, weight = _idw(xyz, new_xyz, offset, new_offset, k)
-    new_feat = _buf((new_xyz.shape[0], feat.shape[1]), feat)
-    for i in range(k):
-        new_feat += feat[idx[:, i].long(), :] * weight[:, i].unsqueeze(-1)
-    return new_feat
+    out = _buf((new_xyz.shape[0], feat.shape[1]), feat)
+    for rank in range(k):
+        out += feat[idx[:, rank].long(), :] * weight[:, rank].unsqueeze(-1)
+    return out
 
 
 class Interpolation(Function):
