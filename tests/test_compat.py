@@ -19,7 +19,12 @@ def test_install_tier1_registers_extension_modules():
                      "gather_points_grad_wrapper", "furthest_point_sampling_wrapper", "three_nn_wrapper",
                      "three_interpolate_wrapper", "three_interpolate_grad_wrapper"):
             assert callable(getattr(pointnet2_batch_cuda, name))
-        assert callable(pointops_cuda.knnquery_cuda)
+        # every export of pointops_api.cpp:13-25
+        for name in ("furthestsampling_cuda", "knnquery_cuda", "ballquery_cuda", "grouping_forward_cuda",
+                     "grouping_backward_cuda", "interpolation_forward_cuda", "interpolation_backward_cuda",
+                     "subtraction_forward_cuda", "subtraction_backward_cuda", "aggregation_forward_cuda",
+                     "aggregation_backward_cuda"):
+            assert callable(getattr(pointops_cuda, name))
     finally:
         for k, v in saved.items():
             if v is None:
