@@ -13,7 +13,7 @@
 //
 //   1. bbox            one pass, block reduce + ordered-int atomics
 //   2. cell sort       points are binned into a 2^b x 2^b x 2^b grid, cells numbered along a
-//                      Morton curve, and counting-sorted (histogram -> single-CTA scan ->
+//                      Hilbert curve, and counting-sorted (histogram -> single-CTA scan ->
 //                      scatter) into a float4 {x, y, z, original index} array.  The grid is
 //                      ONLY a locality heuristic: correctness never depends on it.
 //   3. tile AABBs      every 128 consecutive sorted points form a tile with an exact bounding
@@ -104,7 +104,7 @@ __global__ void bbox_init_kernel(int nb, uint32_t *bb) {
 }
 
 // ---------------------------------------------------------------------------------------
-// 2. Morton cell of a point (clamped into the grid; NaN -> cell 0)
+// 2. cell of a point along the space-filling curve (clamped into the grid; NaN -> cell 0)
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t spread3(uint32_t v) {   // 10 bits -> every third bit
     v = (v | (v << 16)) & 0x030000ffu;
@@ -112,6 +112,36 @@ __device__ __forceinline__ uint32_t spread3(uint32_t v) {   // 10 bits -> every 
     v = (v | (v << 4)) & 0x030c30c3u;
     v = (v | (v << 2)) & 0x09249249u;
     return v;
+}
+
+// Position of grid cell (c[0], c[1], c[2]) along a 3-D Hilbert curve of `bits` levels (Skilling's
+// transposition, "Programming the Hilbert curve", 2004).  Unlike the Morton order the Hilbert order has
+// no jumps — consecutive cells always share a face — so a run of 128 consecutive sorted points is a
+// compact patch and its bounding box is tight; along the Morton curve a run that straddles a jump has a
+// box covering everything in between, which every query nearby must then evaluate.  Any bijection of
+// the cells onto [0, 8^bits) would give identical search results; this one gives the fewest tile visits.
+__device__ __forceinline__ uint32_t hilbert_of(uint32_t c0, uint32_t c1, uint32_t c2, int bits) {
+    uint32_t X[3] = {c0, c1, c2};
+    const uint32_t M = 1u << (bits - 1);
+    for (uint32_t Q = M; Q > 1; Q >>= 1) {
+        const uint32_t P = Q - 1;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (X[i] & Q) X[0] ^= P;
+            else {
+                const uint32_t t = (X[0] ^ X[i]) & P;
+                X[0] ^= t;
+                X[i] ^= t;
+            }
+        }
+    }
+    X[1] ^= X[0];
+    X[2] ^= X[1];
+    uint32_t t = 0;
+    for (uint32_t Q = M; Q > 1; Q >>= 1)
+        if (X[2] & Q) t ^= Q - 1;
+    X[0] ^= t; X[1] ^= t; X[2] ^= t;
+    return (spread3(X[0]) << 2) | (spread3(X[1]) << 1) | spread3(X[2]);
 }
 
 __device__ __forceinline__ uint32_t cell_of(float x, float y, float z, const uint32_t *__restrict__ bb, int bits) {
@@ -126,7 +156,11 @@ __device__ __forceinline__ uint32_t cell_of(float x, float y, float z, const uin
         t = fminf(fmaxf(t, 0.f), (float)(G - 1));      // also maps NaN to 0 (fmaxf(NaN,0) = 0)
         c[a] = (uint32_t)t;
     }
+#ifdef AMC3D_MORTON
     return spread3(c[0]) | (spread3(c[1]) << 1) | (spread3(c[2]) << 2);
+#else
+    return hilbert_of(c[0], c[1], c[2], bits);
+#endif
 }
 
 __global__ void __launch_bounds__(256)
@@ -624,8 +658,8 @@ knn_tq_kernel(Geom gs, int m, int mpad, int self, const float4 *__restrict__ sp,
     }
 
     // ---- the box of the warp's queries and the loosest bound among them: a cheap first filter, lanes over
-    // boxes; what passes it is tested exactly, lanes over queries (a run of 32 queries along the Morton curve
-    // may straddle a jump of the curve, and then its box says little) -------------------------------------
+    // boxes; what passes it is tested exactly, lanes over queries (a run of 32 queries along the curve
+    // may span a bend of the curve, and then its box says little) -------------------------------------
     float wlo[3] = {qx, qy, qz}, whi[3] = {qx, qy, qz};
 #pragma unroll
     for (int c = 0; c < 3; ++c)
@@ -869,7 +903,7 @@ static int pick_bits(int n) {
     return b;
 }
 
-// sort nb clouds of `count` points each into Morton-cell order, cloud b at [b*cpad, b*cpad + count);
+// sort nb clouds of `count` points each into curve-cell order, cloud b at [b*cpad, b*cpad + count);
 // returns cell_start (exclusive starts over all clouds, unpadded) if wanted
 static float4 *sort_points(Scratch &ws, int nb, int count, int cpad, const float *xyz, const uint32_t *bb, int bits,
                            int **cell_start_out) {
