@@ -995,12 +995,15 @@ int knn_grid_batched(int nb, int n, int m, int nsample, const float *xyz, const 
     search_grid(B, m, qpw, blocks);
 #define KNN_WQ_ARGS B.gs, m, B.mpad, nsample, B.self, qpw, B.sp, B.tlo, B.thi, B.glo, B.ghi, B.sq, B.cell_start, B.bb, idx, dist2, order_out
 #define KNN_TQ_ARGS B.gs, m, B.mpad, B.self, B.sp, B.tlo, B.thi, B.glo, B.ghi, B.sq, B.cell_start, B.bb, idx, dist2, order_out
-    // Few neighbours for queries much denser than the support (three_nn onto the next finer level: 4 queries
-    // per known point): thread per query.  Measured at config 2: 0.21 ms against 0.39 ms for the 192 000-query
-    // three_nn; with queries as sparse as the support (self searches) or fewer than ~4000 query warps the
-    // warp-per-query kernel wins, whatever k.  AMC3D_KNN_TQ_MAX = 0 switches it off for measurements.
+    // Few neighbours and queries at least as dense as the support (three_nn onto the next finer level: 4
+    // queries per known point; self searches with k <= 4): thread per query.  Measured at config-2 shapes
+    // (Hilbert order): 192 000-query three_nn 0.19 ms against 0.39 ms; self search of 192 000 / 96 000 points
+    // with k = 3: 0.26 / 0.15 ms against 0.31 / 0.19 ms.  The warp-per-query kernel wins for queries sparser
+    // than the support (k = 4 label vote, 48 000 queries in 192 000 points: 0.19 against 0.30 ms), below
+    // ~2 000 query warps (the slowest warp sets the time) and for k > 4 (k = 8: 0.84 against 0.53 ms).
+    // AMC3D_KNN_TQ_MAX = 0 switches it off for measurements.
     static const int tq_max = getenv("AMC3D_KNN_TQ_MAX") ? atoi(getenv("AMC3D_KNN_TQ_MAX")) : 4;
-    if (nsample <= tq_max && nsample <= 4 && m >= 2 * n && (long long)nb * B.mpad >= 128 * 1024) {
+    if (nsample <= tq_max && nsample <= 4 && m >= n && (long long)nb * B.mpad >= 64 * 1024) {
         const int tblocks = (int)div_up_ll((long long)nb * B.mpad, TQ_WARPS * 32);
         switch (nsample) {
             case 1: knn_tq_kernel<1><<<tblocks, TQ_WARPS * 32, 0, st>>>(KNN_TQ_ARGS); break;

@@ -244,6 +244,15 @@ def test_knn_dense_queries_thread_per_query_path(k):
     _check_knn(idx.cpu().numpy(), d2.cpu().numpy(), k, sup, xyz, o, qo, sqrt=False)
 
 
+def test_knn_self_small_k_thread_per_query_path():
+    """self search, k <= 4, >= 64k points: also served by the thread-per-query kernel"""
+    from amcontrast3d_b200 import _amloss
+    xyz, _ = scenes.volume_scene(66000, seed=21)
+    o = np.array([66000], np.int32)
+    idx, d2 = _amloss.knn_raw(3, _t(xyz), None, _t(o), _t(o))
+    _check_knn(idx.cpu().numpy(), d2.cpu().numpy(), 3, xyz, xyz, o, o, sqrt=False)
+
+
 def test_three_interpolate_forward_backward():
     from amcontrast3d_b200.layers import three_interpolate, three_interpolation
     rng = np.random.default_rng(2)

@@ -30,6 +30,25 @@ def test_knn_vs_reference_kernel():
         assert torch.equal(i[tie_free], ri[tie_free])
 
 
+def test_knn_small_k_vs_reference_kernel():
+    """k <= 4 with >= 64k query slots goes through the thread-per-query search (self and dense queries)"""
+    from amcontrast3d_b200 import _amloss
+    xyz, _ = scenes.batch_of_scenes(4, 24000, "surface", first_scene=55)
+    flat = _t(xyz.reshape(-1, 3))
+    o = _t(np.array([96000], dtype=np.int32))
+    sup = flat[::6].contiguous()
+    so = _t(np.array([sup.shape[0]], dtype=np.int32))
+    for k in (1, 2, 3, 4):
+        for s_xyz, s_off in ((flat, o), (sup, so)):
+            ri, rd = rk.knnquery(k, s_xyz, flat, s_off, o)
+            _, rdp = rk.knnquery(k + 1, s_xyz, flat, s_off, o)
+            i, d = _amloss.knn_raw(k, s_xyz, flat, s_off, o)
+            assert torch.equal(d, rd)
+            tie_free = (rdp[:, 1:] > rdp[:, :-1]).all(1)
+            assert tie_free.float().mean() > 0.98
+            assert torch.equal(i[tie_free], ri[tie_free])
+
+
 def test_fps_ball_three_nn_vs_reference_kernels():
     from amcontrast3d_b200.layers import ball_query, furthest_point_sample, three_nn
     xyz, _ = scenes.batch_of_scenes(4, 24000, "surface", first_scene=60)
