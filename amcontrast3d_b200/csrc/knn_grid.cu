@@ -327,7 +327,10 @@ __device__ __forceinline__ float point_box2(float x, float y, float z, const flo
 }
 
 constexpr int WQ_WARPS = 8;     // warps per CTA
-constexpr int WQ_QPW_MAX = 16;  // consecutive sorted queries per warp (tile reuse through L1)
+constexpr int WQ_QPW_MAX = 1;   // consecutive sorted queries per warp.  One: measured 16 -> 2 -> 1 at config 2: kNN
+                                // 1.37 -> 1.32 -> 1.24 ms, ball queries 0.97 -> 0.86 -> 0.86 ms (shorter tail of the
+                                // last wave; neighbouring warps share the tiles through L1 just as well).
+                                // AMC3D_KNN_QPW overrides.
 constexpr int TG = 32;          // tiles per box group (second culling level)
 
 // Sorted (ascending) list of S = 32*E entries distributed over the warp: lane l holds slots
@@ -979,7 +982,8 @@ static void search_grid(const Built &B, int m, int &qpw, int &blocks) {
     // enough warps to fill the machine a few times over; long runs of consecutive queries per warp
     // only when there are plenty of queries
     const long long slots = (long long)B.gs.nb * B.mpad;
-    qpw = (int)max(1ll, min((long long)WQ_QPW_MAX, slots / (kNumSMs * WQ_WARPS * 8)));
+    static const int qmax = getenv("AMC3D_KNN_QPW") ? atoi(getenv("AMC3D_KNN_QPW")) : WQ_QPW_MAX;
+    qpw = (int)max(1ll, min((long long)qmax, slots / (kNumSMs * WQ_WARPS * 8)));
     blocks = (int)div_up_ll(slots, WQ_WARPS * qpw);
 }
 
