@@ -127,8 +127,12 @@ class ContrastHead(nn.Module):
         side stream next to the encoder.  `stageACE_list[stages][s]` needs 'p_out' and 'offset' for s = 0
         and s = i only.  Put the returned objects in stageACE_list['am_geometry'] (a list indexed by stage,
         None = compute as usual) and forward() uses them; results are identical."""
-        return _stage_ambiguity(ambiguity_args.stages, i, stageACE_list, target, num_classes, ignore_index,
-                                ambiguity_args, self.nstride, self.ftype)
+        st = _stage_ambiguity(ambiguity_args.stages, i, stageACE_list, target, num_classes, ignore_index,
+                              ambiguity_args, self.nstride, self.ftype)
+        # off the critical path there is time to drop the anchors the loss will not select from the visiting
+        # order, which keeps the forward kernel's warps full (narrow stages put several anchors in a warp)
+        st['order'] = _amloss.compact_order(st['order'], st['a'])
+        return st
 
     def point_contrast_margin(self, n, i, stageACE_list, target, num_classes, ignore_index, ambiguity_args):
         """One stage (MarginContrast.py:220-259) -> (loss, output_ai, target_ai)."""

@@ -142,7 +142,8 @@ class AMLossFunction(Function):
         m, d = f.shape
         dev = f.device
         inv = torch.empty((m,), dtype=torch.float32, device=dev)
-        loss_pt = torch.empty((m,), dtype=torch.float32, device=dev)
+        # zero-filled: with a compacted `order` (see compact_order) the kernel never visits unselected anchors
+        loss_pt = torch.zeros((m,), dtype=torch.float32, device=dev)
         ghat = torch.zeros((m, d), dtype=torch.float32, device=dev)
         loss = torch.empty((), dtype=torch.float32, device=dev)
         with _capi.guard(f):
@@ -165,6 +166,21 @@ class AMLossFunction(Function):
             _capi.call("amc3d_amloss_backward", m, d, ptr(f), ptr(inv), ptr(ghat), ptr(up), ptr(stats), 0,
                        ptr(grad_f), stream(f))
         return grad_f, None, None, None, None, None, None
+
+
+def compact_order(order, a):
+    """The visiting order with the anchors the loss does not select (a outside (0, 1]) removed: selected
+    anchors first, in their original relative order, then -1 up to the original length.  The forward kernel
+    skips negative entries, so its warps are full of selected anchors instead of being kept alive by one
+    selected anchor among several (43 % of the stage-0 anchors are selected at config 2, 67 % of the warps
+    had at least one).  Static shapes, no host synchronisation: capturable."""
+    m = order.numel()
+    keep = torch.logical_and(a > 0, a <= 1)[order.long()]
+    slot = torch.cumsum(keep, 0) - 1
+    slot = torch.where(keep, slot, torch.full_like(slot, m))          # dropped anchors go to a dump slot
+    out = torch.full((m + 1,), -1, dtype=torch.int32, device=order.device)
+    out.scatter_(0, slot, order)
+    return out[:m]
 
 
 def am_loss(f, nl, posbits, a, stats, args, order=None):

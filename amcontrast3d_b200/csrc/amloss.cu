@@ -215,9 +215,15 @@ amloss_forward_kernel(int m, int ke, int ld, const float *__restrict__ f, const 
     const long long slot = ((long long)blockIdx.x * 256 + threadIdx.x) / G;
     // all lanes of a group share i; whole groups exit together.  Shuffles below use the full
     // mask, so a partially filled last warp keeps its idle groups alive until the end.
-    const bool in_range = slot < m;
-    // anchors are visited in `order` (spatially coherent): neighbouring groups then gather the same rows
-    const long long i = (in_range && order != nullptr) ? __ldg(order + slot) : slot;
+    // anchors are visited in `order` (spatially coherent): neighbouring groups then gather the same rows.
+    // A negative entry is an empty slot: callers may pass the order with the unselected anchors removed and
+    // the tail filled with -1 (loss_pt pre-zeroed), so that every live warp is full of selected anchors.
+    bool in_range = slot < m;
+    long long i = slot;
+    if (in_range && order != nullptr) {
+        i = __ldg(order + slot);
+        in_range = i >= 0;
+    }
     const float ai = in_range ? __ldg(a + i) : 0.f;
     const bool sel = in_range && (0.f < ai) && (ai <= 1.f);
     if (in_range && !sel && g == 0) loss_pt[i] = 0.f;
