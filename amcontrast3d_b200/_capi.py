@@ -42,6 +42,7 @@ SIGNATURES = {
     "amc3d_version": [],
     "amc3d_arch": [],
     "amc3d_last_error": [],
+    "amc3d_trim_scratch": [ctypes.c_size_t],
     "amc3d_furthest_point_sampling": [_I, _I, _I, _P, _P, _P, _P],
     "amc3d_ball_query": [_I, _I, _I, _F, _I, _P, _P, _P, _P],
     "amc3d_group_points": [_I, _I, _I, _I, _I, _P, _P, _P, _P],
@@ -101,11 +102,19 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     with _lock:
         if _lib is not None:
             return _lib
-        path = os.environ.get("AMC3D_LIB") or _build.LIBPATH      # AMC3D_LIB: an experimental build of the same ABI
-        if not os.path.exists(path):
-            if not build_if_missing:
-                raise Amc3dError(f"{path} is missing: run `python -m amcontrast3d_b200._build`")
-            _build.build()
+        path = os.environ.get("AMC3D_LIB")                        # AMC3D_LIB: an experimental build of the same ABI
+        if not path:
+            path = _build.LIBPATH
+            # never load a library that was built from other sources than the ones next to it: the digest
+            # stamp is written beside the artefact by the build (both untracked), so a checkout that
+            # changes csrc/ makes is_current() false until the library is rebuilt
+            if not _build.is_current():
+                if not build_if_missing:
+                    what = "is missing" if not os.path.exists(path) else "is stale (csrc/ or include/amc3d.h changed since it was built)"
+                    raise Amc3dError(f"{path} {what}: run `python -m amcontrast3d_b200._build`")
+                _build.build()
+        elif not os.path.exists(path):
+            raise Amc3dError(f"AMC3D_LIB={path} does not exist")
         lib = ctypes.CDLL(path)
         for name, argtypes in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError = the library does not match the header

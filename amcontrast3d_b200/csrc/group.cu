@@ -664,7 +664,12 @@ static int group_impl() {
 static int group_common(bool fwd, int b, int c, int n, long long P, const float *src, const int *idx,
                         float *dst, float *workspace, cudaStream_t st, const char *what, int nsample = 0,
                         bool overwrite = false) {
-    if (b == 0 || c == 0 || P == 0) return 0;
+    if (b == 0 || c == 0 || P == 0) {
+        // nothing to scatter: the overwriting variants still owe the caller a zero gradient (torch.empty there)
+        if (!fwd && overwrite && (size_t)b * n * c > 0)
+            cudaMemsetAsync(dst, 0, sizeof(float) * (size_t)b * n * c, st);
+        return check_launch(what);
+    }
     AMC3D_REQUIRE(b <= 65535, AMC3D_ELIMIT, "%s: batch %d > 65535", what, b);
     AMC3D_REQUIRE(P < (1ll << 31), AMC3D_ELIMIT, "%s: npoints*nsample too large", what);
     const bool aligned = (P % 8 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) &&
@@ -823,7 +828,11 @@ static int interp_grad_common(int b, int c, int n, int m, const float *grad_out,
                               bool overwrite) {
     AMC3D_REQUIRE(b >= 0 && c >= 0 && m >= 0 && n >= 0, AMC3D_EINVAL, "three_interpolate_grad: negative size");
     AMC3D_REQUIRE(b <= 65535, AMC3D_ELIMIT, "three_interpolate_grad: batch %d > 65535", b);
-    if (b == 0 || c == 0 || n == 0) return 0;
+    if (b == 0 || c == 0 || n == 0) {
+        if (overwrite && (size_t)b * m * c > 0)
+            cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)b * m * c, as_stream(stream));
+        return check_launch("three_interpolate_grad");
+    }
     if (workspace != nullptr && c >= 8 && c % 4 == 0 && n % 4 == 0 && m > 0 && al16(grad_out) && group_impl() >= 1) {
         cudaStream_t st = as_stream(stream);
         cudaMemsetAsync(workspace, 0, sizeof(float) * (size_t)b * m * c, st);

@@ -317,11 +317,12 @@ extern "C" int amc3d_knnquery_order(int n, int m, int nseg, int nsample, const f
     } else {
         const int blocks = div_up(m, KNN_BIG_THREADS);
         const size_t smem = sizeof(float4) * KNN_GROUPS * 3 + (size_t)nsample * KNN_BIG_THREADS * 8;
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(knn_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(sizeof(float4) * KNN_GROUPS * 3 + 128 * KNN_BIG_THREADS * 8));
-            attr_set = true;
+        // the opt-in is per device and a process may drive several: set it on every call (cheap, host-only)
+        const cudaError_t ae = cudaFuncSetAttribute(knn_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    (int)(sizeof(float4) * KNN_GROUPS * 3 + 128 * KNN_BIG_THREADS * 8));
+        if (ae != cudaSuccess) {
+            set_error("knnquery: cudaFuncSetAttribute: %s", cudaGetErrorString(ae));
+            return (int)ae;
         }
         knn_smem_kernel<<<blocks, KNN_BIG_THREADS, smem, st>>>(n, m, nseg, nsample, xyz, new_xyz, offset,
                                                                new_offset, idx, dist2);

@@ -864,20 +864,45 @@ group_aabb_kernel(int ntb, int ngb, int ngroups, const float4 *__restrict__ tlo,
     }
 }
 
-// The default memory pool hands freed memory back to the driver at every synchronisation point
-// unless a release threshold is set — a trainer that reads the loss each step (loss.item())
-// would otherwise pay a fresh physical allocation for every scratch buffer of every kNN call
-// (measured: 96 ms per step instead of 22 ms).  Keep the pool's memory: set once per device.
-static void keep_pool_memory() {
-    static bool done[64] = {};
+// Scratch comes from a PRIVATE stream-ordered pool per device, owned by this library, never from the
+// device's default pool: a pool hands freed memory back to the driver at every synchronisation point
+// unless a release threshold is set — a trainer that reads the loss each step (loss.item()) would
+// otherwise pay a fresh physical allocation for every scratch buffer of every search call (measured:
+// 96 ms per step instead of 22 ms) — and raising the threshold of the default pool would change the
+// behaviour of every other cudaMallocAsync user in the host process.  The private pool keeps what the
+// largest search needed (bounded by the caller's problem sizes; amc3d_trim_scratch() returns it).
+static cudaMemPool_t g_pool[64] = {};
+static cudaError_t scratch_pool(cudaMemPool_t *out) {
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (g_pool[dev] == nullptr) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool;
+        e = cudaMemPoolCreate(&pool, &props);
+        if (e != cudaSuccess) return e;
         unsigned long long thr = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        if (e != cudaSuccess) return e;
+        g_pool[dev] = pool;
     }
-    done[dev] = true;
+    *out = g_pool[dev];
+    return cudaSuccess;
+}
+
+// Give the scratch the searches have cached on the current device back to the driver (keeps `keep_bytes`).
+extern "C" int amc3d_trim_scratch(size_t keep_bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess && (dev < 0 || dev >= 64)) e = cudaErrorInvalidDevice;
+    if (e == cudaSuccess && g_pool[dev] != nullptr) e = cudaMemPoolTrimTo(g_pool[dev], keep_bytes);
+    if (e != cudaSuccess) set_error("trim_scratch: %s", cudaGetErrorString(e));
+    return (int)e;
 }
 
 // per-stream scratch, stream-ordered (cudaMallocAsync pools make this cheap after warm-up)
@@ -886,12 +911,13 @@ struct Scratch {
     void *ptrs[24];
     int count = 0;
     cudaError_t err = cudaSuccess;
-    explicit Scratch(cudaStream_t s) : st(s) { keep_pool_memory(); }
+    cudaMemPool_t pool = nullptr;
+    explicit Scratch(cudaStream_t s) : st(s) { err = scratch_pool(&pool); }
     template <class T>
     T *get(size_t n) {
         void *p = nullptr;
         if (err == cudaSuccess && count >= 24) err = cudaErrorMemoryAllocation;
-        if (err == cudaSuccess) err = cudaMallocAsync(&p, n * sizeof(T) + 16, st);
+        if (err == cudaSuccess) err = cudaMallocFromPoolAsync(&p, n * sizeof(T) + 16, pool, st);
         if (err == cudaSuccess) ptrs[count++] = p;
         return reinterpret_cast<T *>(p);
     }

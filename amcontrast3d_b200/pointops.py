@@ -140,9 +140,9 @@ def querygroup(nsample, xyz, new_xyz, feat, offset, new_offset, radius=None, que
     if new_xyz is None:
         new_xyz = xyz
     if idx is not None:
-        # the reference only forms the groups when it ran the search itself; with a caller-provided idx
-        # its locals are unbound (pointops.py:157) — raise the same way, with a message
-        raise UnboundLocalError("querygroup: idx given by the caller — the reference forms no groups in this case")
+        # the reference's whole body, `return` included, sits under `if idx is None` (pointops.py:125-152):
+        # with a caller-provided idx it falls off the end and returns None — and so does this
+        return None
     if nsample is None:                                         # "group everything": no search at all
         return xyz.transpose(1, 2).unsqueeze(2), (None if feat is None else feat.unsqueeze(2))
     use_knn = query_method in ('knn', 'knnquery')

@@ -14,9 +14,18 @@ from . import _capi
 from ._capi import ptr, stream
 
 
+def _off(t):
+    """Segment offsets as the kernels read them: contiguous int32 on the device (the reference's kernels
+    reinterpret whatever they are given as int*; an int64 tensor would silently be misread)."""
+    if t.dtype != torch.int32:
+        t = t.to(torch.int32)
+    return t.contiguous()
+
+
 def knnquery_cuda(m, nsample, xyz, new_xyz, offset, new_offset, idx, dist2):
     """ref: knnquery_cuda.cpp:7.  idx (m,nsample) i32 and dist2 (m,nsample) f32 (SQUARED) are
     written in place."""
+    offset, new_offset = _off(offset), _off(new_offset)
     with _capi.guard(xyz):
         _capi.call("amc3d_knnquery", int(xyz.shape[0]), int(m), int(offset.shape[0]), int(nsample),
                    ptr(xyz), ptr(new_xyz), ptr(offset), ptr(new_offset), ptr(idx), ptr(dist2),
@@ -50,6 +59,7 @@ def furthestsampling_cuda(b, n_max, xyz, offset, new_offset, tmp, idx):
 
 def ballquery_cuda(m, radius, nsample, xyz, new_xyz, offset, new_offset, idx):
     """ref: ballquery_cuda.cpp:35.  idx (m,nsample) i32, zero-filled by the caller."""
+    offset, new_offset = _off(offset), _off(new_offset)
     with _capi.guard(xyz):
         _capi.call("amc3d_pointops_ballquery", int(xyz.shape[0]), int(m), int(offset.shape[0]), float(radius),
                    int(nsample), ptr(xyz), ptr(new_xyz), ptr(offset), ptr(new_offset), ptr(idx), stream(xyz))

@@ -19,6 +19,7 @@
 #ifndef AMC3D_H
 #define AMC3D_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -35,6 +36,12 @@ int amc3d_version(void);
 const char *amc3d_arch(void);
 /* text of the last error on this thread (never NULL) */
 const char *amc3d_last_error(void);
+/* The culled searches (knnquery, ball_query, three_nn on clouds of >= 2048 points) take their
+ * scratch, stream-ordered, from a memory pool PRIVATE to this library (one per device, created on
+ * first use); the pool keeps what the largest call needed so that later calls do not allocate.
+ * amc3d_trim_scratch returns everything above `keep_bytes` on the current device to the driver.
+ * No other global state: nothing here touches the device's default memory pool. */
+int amc3d_trim_scratch(size_t keep_bytes);
 
 /* ---------------------------------------------------------------------------------------
  * pointnet2_batch family: batched (B,N,3) xyz and (B,C,N) features, all contiguous f32/i32
@@ -146,6 +153,10 @@ int amc3d_three_interpolate_grad_ws_set(int b, int c, int n, int m, const float 
  * reference's hard limit is 100, knnquery_cuda_kernel.cu:86-87).
  * `n` and `nseg` are the sizes of xyz and offset, which the reference launcher does not
  * take (it trusts the offsets); the Python shim passes xyz.shape[0] and offset.shape[0].
+ * Contract for nseg == 1 (what AMContrast3D always passes): the one segment IS the whole
+ * array, i.e. offset[0] == n and new_offset[0] == m; the culled search does not read the two
+ * device arrays in that case (reading them would cost a host synchronisation).  A caller that
+ * pads xyz beyond offset[0] must pass n = offset[0].  offset/new_offset must be int32.
  * ref: pointops/src/knnquery/knnquery_cuda.cpp:7 knnquery_cuda,
  *      knnquery_cuda_kernel.cu:111 knnquery_cuda_launcher */
 int amc3d_knnquery(int n, int m, int nseg, int nsample, const float *xyz, const float *new_xyz,
