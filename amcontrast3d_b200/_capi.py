@@ -43,6 +43,8 @@ SIGNATURES = {
     "amc3d_arch": [],
     "amc3d_last_error": [],
     "amc3d_trim_scratch": [ctypes.c_size_t],
+    "amc3d_fp32_probe": [_I, _I, _P, POINTER(ctypes.c_double), _P],
+    "amc3d_search_stats": [_P],
     "amc3d_furthest_point_sampling": [_I, _I, _I, _P, _P, _P, _P],
     "amc3d_ball_query": [_I, _I, _I, _F, _I, _P, _P, _P, _P],
     "amc3d_group_points": [_I, _I, _I, _I, _I, _P, _P, _P, _P],
@@ -136,6 +138,8 @@ def check(rc: int, name: str) -> None:
 LAUNCHES = 0
 # when set to a list, every call appends (name, start_event, stop_event) recorded on the launch stream
 PROFILE = None
+# measurement hook: when set, called as AFTER_CALL(name, args) after every entry point (bench.py's pair counting)
+AFTER_CALL = None
 
 
 def _kernels_in(name: str, args) -> int:
@@ -174,6 +178,8 @@ def call(name: str, *args) -> None:
         check(fn(*args), name)
         e1.record(st)
         PROFILE.append((name, e0, e1, args[:6]))
+    if AFTER_CALL is not None:
+        AFTER_CALL(name, args)
     LAUNCHES += _kernels_in(name, args)
 
 

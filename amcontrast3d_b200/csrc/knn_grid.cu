@@ -406,13 +406,16 @@ struct Geom {
     int bits;    // grid bits per axis
 };
 
-template <int E>
+// STATS: count the distance evaluations actually issued (tiles visited x GT) into stats[0..1] — a separate
+// instantiation, launched only while amc3d_search_stats() has a counter array registered (bench.py's
+// "evaluated pairs" figure), so the production kernels carry no trace of it.
+template <int E, bool STATS = false>
 __global__ void __launch_bounds__(WQ_WARPS * 32)
 knn_wq_kernel(Geom gs, int m, int mpad, int nsample, int self, int qpw, const float4 *__restrict__ sp,
               const float4 *__restrict__ tlo, const float4 *__restrict__ thi, const float4 *__restrict__ glo,
               const float4 *__restrict__ ghi, const float4 *__restrict__ sq, const int *__restrict__ cell_start,
               const uint32_t *__restrict__ bb, int *__restrict__ idx, float *__restrict__ dist2,
-              int *__restrict__ order_out) {
+              int *__restrict__ order_out, unsigned long long *__restrict__ stats) {
     const int lane = threadIdx.x & 31;
     const int wq0 = (blockIdx.x * WQ_WARPS + (threadIdx.x >> 5)) * qpw;
     const int n = gs.n;
@@ -423,6 +426,7 @@ knn_wq_kernel(Geom gs, int m, int mpad, int nsample, int self, int qpw, const fl
         const int b = gs.nb == 1 ? 0 : q / mpad;
         if (q - b * mpad >= m) continue;                      // padding slot of the query layout
         const float4 me = __ldg(sq + q);
+        int ntiles = 1;                                       // STATS only: tiles evaluated for this query (seed = 1)
         // the visiting order (spatially coherent) for callers that want to process the queries the same way
         if (order_out != nullptr && lane == 0) order_out[(long long)b * m + (q - b * mpad)] = __float_as_int(me.w);
         const float qx = me.x, qy = me.y, qz = me.z;
@@ -462,6 +466,7 @@ knn_wq_kernel(Geom gs, int m, int mpad, int nsample, int self, int qpw, const fl
             float dd[GR];
             int oi[GR];
             eval_tile(t, dd, oi);
+            if (STATS) ++ntiles;
 #pragma unroll
             for (int r = 0; r < GR; ++r) {
                 bool cand = lex_lt(dd[r], oi[r], td, ti);
@@ -551,6 +556,10 @@ knn_wq_kernel(Geom gs, int m, int mpad, int nsample, int self, int qpw, const fl
                 dist2[qorig * nsample + s] = best.d[e];
             }
         }
+        if (STATS && lane == 0) {
+            atomicAdd(stats + 0, (unsigned long long)ntiles * GT);
+            atomicAdd(stats + 1, 1ull);
+        }
     }
 }
 
@@ -572,13 +581,15 @@ __device__ __forceinline__ float box_box2(const float (&alo)[3], const float (&a
 
 constexpr int TQ_WARPS = 4;
 
-template <int K>
+template <int K, bool STATS = false>
 __global__ void __launch_bounds__(TQ_WARPS * 32)
 knn_tq_kernel(Geom gs, int m, int mpad, int self, const float4 *__restrict__ sp, const float4 *__restrict__ tlo,
               const float4 *__restrict__ thi, const float4 *__restrict__ glo, const float4 *__restrict__ ghi,
               const float4 *__restrict__ sq, const int *__restrict__ cell_start, const uint32_t *__restrict__ bb,
-              int *__restrict__ idx, float *__restrict__ dist2, int *__restrict__ order_out) {
+              int *__restrict__ idx, float *__restrict__ dist2, int *__restrict__ order_out,
+              unsigned long long *__restrict__ stats) {
     const int lane = threadIdx.x & 31;
+    int ntiles = 0;                                   // STATS only
     const long long q0 = ((long long)blockIdx.x * TQ_WARPS + (threadIdx.x >> 5)) * 32;   // first query slot of the warp
     if (q0 >= (long long)gs.nb * mpad) return;
     const int b = (int)(q0 / mpad);                   // mpad is a multiple of 32: one cloud per warp
@@ -606,6 +617,7 @@ knn_tq_kernel(Geom gs, int m, int mpad, int self, const float4 *__restrict__ sp,
     auto process_tile = [&](int t) {
         const int cnt = min(GT, n - (t - tb0) * GT);   // warp-uniform
         const float4 *tp = sp + (long long)t * GT;
+        if (STATS) ++ntiles;
         float4 v[GR];
 #pragma unroll
         for (int r = 0; r < GR; ++r)                   // +inf coordinates: distance +inf, never accepted
@@ -709,6 +721,10 @@ knn_tq_kernel(Geom gs, int m, int mpad, int self, const float4 *__restrict__ sp,
             dist2[row + e] = bd[e];
         }
     }
+    if (STATS && lane == 0) {                         // every lane evaluates every point of a visited tile
+        atomicAdd(stats + 2, (unsigned long long)ntiles * GT * 32);
+        atomicAdd(stats + 3, 32ull);
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -740,12 +756,12 @@ struct WarpIdxList {
     }
 };
 
-template <int E>
+template <int E, bool STATS = false>
 __global__ void __launch_bounds__(WQ_WARPS * 32)
 ball_wq_kernel(Geom gs, int m, int mpad, float radius, int nsample, int self, int qpw, const float4 *__restrict__ sp,
                const float4 *__restrict__ tlo, const float4 *__restrict__ thi, const float4 *__restrict__ glo,
                const float4 *__restrict__ ghi, const float4 *__restrict__ sq, const int *__restrict__ cell_start,
-               const uint32_t *__restrict__ bb, int *__restrict__ idx) {
+               const uint32_t *__restrict__ bb, int *__restrict__ idx, unsigned long long *__restrict__ stats) {
     const int lane = threadIdx.x & 31;
     const int wq0 = (blockIdx.x * WQ_WARPS + (threadIdx.x >> 5)) * qpw;
     const int n = gs.n;
@@ -762,9 +778,11 @@ ball_wq_kernel(Geom gs, int m, int mpad, float radius, int nsample, int self, in
         best.init(nsample, lane);
         int ti = 0x7fffffff;                                  // current nsample-th smallest hit index
         const int tb0 = b * gs.ntb;
+        int ntiles = 0;                                       // STATS only
 
         auto process_tile = [&](int t) {
             const int left = n - (t - tb0) * GT;               // >= GT for all but the last tile of a cloud
+            if (STATS) ++ntiles;
 #pragma unroll
             for (int r = 0; r < GR; ++r) {
                 bool cand = false;
@@ -825,6 +843,10 @@ ball_wq_kernel(Geom gs, int m, int mpad, float radius, int nsample, int self, in
         for (int e = 0; e < E; ++e) {
             const int v = __shfl_sync(0xffffffffu, best.i[e], shift / E);
             if (e == shift % E) first = v;
+        }
+        if (STATS && lane == 0) {
+            atomicAdd(stats + 4, (unsigned long long)ntiles * GT);
+            atomicAdd(stats + 5, 1ull);
         }
         if (first == 0x7fffffff) continue;                    // no hit: the row keeps the caller's zeros
         const long long qorig = (long long)b * m + __float_as_int(me.w);
@@ -893,6 +915,13 @@ static cudaError_t scratch_pool(cudaMemPool_t *out) {
     }
     *out = g_pool[dev];
     return cudaSuccess;
+}
+
+// Counter array registered by amc3d_search_stats (device, 8 x u64), or NULL: see knn_wq_kernel<E, STATS>.
+static unsigned long long *g_search_stats = nullptr;
+extern "C" int amc3d_search_stats(void *counters) {
+    g_search_stats = static_cast<unsigned long long *>(counters);
+    return 0;
 }
 
 // Give the scratch the searches have cached on the current device back to the driver (keeps `keep_bytes`).
@@ -1023,8 +1052,9 @@ int knn_grid_batched(int nb, int n, int m, int nsample, const float *xyz, const 
     if (e != cudaSuccess) return (int)e;
     int qpw, blocks;
     search_grid(B, m, qpw, blocks);
-#define KNN_WQ_ARGS B.gs, m, B.mpad, nsample, B.self, qpw, B.sp, B.tlo, B.thi, B.glo, B.ghi, B.sq, B.cell_start, B.bb, idx, dist2, order_out
-#define KNN_TQ_ARGS B.gs, m, B.mpad, B.self, B.sp, B.tlo, B.thi, B.glo, B.ghi, B.sq, B.cell_start, B.bb, idx, dist2, order_out
+    unsigned long long *const stats = g_search_stats;
+#define KNN_WQ_ARGS B.gs, m, B.mpad, nsample, B.self, qpw, B.sp, B.tlo, B.thi, B.glo, B.ghi, B.sq, B.cell_start, B.bb, idx, dist2, order_out, stats
+#define KNN_TQ_ARGS B.gs, m, B.mpad, B.self, B.sp, B.tlo, B.thi, B.glo, B.ghi, B.sq, B.cell_start, B.bb, idx, dist2, order_out, stats
     // Few neighbours and queries at least as dense as the support (three_nn onto the next finer level: 4
     // queries per known point; self searches with k <= 4): thread per query.  Measured at config-2 shapes
     // (Hilbert order): 192 000-query three_nn 0.19 ms against 0.39 ms; self search of 192 000 / 96 000 points
@@ -1035,12 +1065,27 @@ int knn_grid_batched(int nb, int n, int m, int nsample, const float *xyz, const 
     static const int tq_max = getenv("AMC3D_KNN_TQ_MAX") ? atoi(getenv("AMC3D_KNN_TQ_MAX")) : 4;
     if (nsample <= tq_max && nsample <= 4 && m >= n && (long long)nb * B.mpad >= 64 * 1024) {
         const int tblocks = (int)div_up_ll((long long)nb * B.mpad, TQ_WARPS * 32);
+        if (stats != nullptr) {                       // measurement run: the counting instantiations
+            switch (nsample) {
+                case 1: knn_tq_kernel<1, true><<<tblocks, TQ_WARPS * 32, 0, st>>>(KNN_TQ_ARGS); break;
+                case 2: knn_tq_kernel<2, true><<<tblocks, TQ_WARPS * 32, 0, st>>>(KNN_TQ_ARGS); break;
+                case 3: knn_tq_kernel<3, true><<<tblocks, TQ_WARPS * 32, 0, st>>>(KNN_TQ_ARGS); break;
+                default: knn_tq_kernel<4, true><<<tblocks, TQ_WARPS * 32, 0, st>>>(KNN_TQ_ARGS); break;
+            }
+            return (int)cudaGetLastError();
+        }
         switch (nsample) {
             case 1: knn_tq_kernel<1><<<tblocks, TQ_WARPS * 32, 0, st>>>(KNN_TQ_ARGS); break;
             case 2: knn_tq_kernel<2><<<tblocks, TQ_WARPS * 32, 0, st>>>(KNN_TQ_ARGS); break;
             case 3: knn_tq_kernel<3><<<tblocks, TQ_WARPS * 32, 0, st>>>(KNN_TQ_ARGS); break;
             default: knn_tq_kernel<4><<<tblocks, TQ_WARPS * 32, 0, st>>>(KNN_TQ_ARGS); break;
         }
+        return (int)cudaGetLastError();
+    }
+    if (stats != nullptr) {
+        if (nsample <= 32) knn_wq_kernel<1, true><<<blocks, WQ_WARPS * 32, 0, st>>>(KNN_WQ_ARGS);
+        else if (nsample <= 64) knn_wq_kernel<2, true><<<blocks, WQ_WARPS * 32, 0, st>>>(KNN_WQ_ARGS);
+        else knn_wq_kernel<4, true><<<blocks, WQ_WARPS * 32, 0, st>>>(KNN_WQ_ARGS);
         return (int)cudaGetLastError();
     }
     if (nsample <= 32) knn_wq_kernel<1><<<blocks, WQ_WARPS * 32, 0, st>>>(KNN_WQ_ARGS);
@@ -1063,7 +1108,14 @@ int ball_grid_batched(int nb, int n, int m, float radius, int nsample, const flo
     if (e != cudaSuccess) return (int)e;
     int qpw, blocks;
     search_grid(B, m, qpw, blocks);
-#define BALL_WQ_ARGS B.gs, m, B.mpad, radius, nsample, B.self, qpw, B.sp, B.tlo, B.thi, B.glo, B.ghi, B.sq, B.cell_start, B.bb, idx
+    unsigned long long *const stats = g_search_stats;
+#define BALL_WQ_ARGS B.gs, m, B.mpad, radius, nsample, B.self, qpw, B.sp, B.tlo, B.thi, B.glo, B.ghi, B.sq, B.cell_start, B.bb, idx, stats
+    if (stats != nullptr) {
+        if (nsample <= 32) ball_wq_kernel<1, true><<<blocks, WQ_WARPS * 32, 0, st>>>(BALL_WQ_ARGS);
+        else if (nsample <= 64) ball_wq_kernel<2, true><<<blocks, WQ_WARPS * 32, 0, st>>>(BALL_WQ_ARGS);
+        else ball_wq_kernel<4, true><<<blocks, WQ_WARPS * 32, 0, st>>>(BALL_WQ_ARGS);
+        return (int)cudaGetLastError();
+    }
     if (nsample <= 32) ball_wq_kernel<1><<<blocks, WQ_WARPS * 32, 0, st>>>(BALL_WQ_ARGS);
     else if (nsample <= 64) ball_wq_kernel<2><<<blocks, WQ_WARPS * 32, 0, st>>>(BALL_WQ_ARGS);
     else ball_wq_kernel<4><<<blocks, WQ_WARPS * 32, 0, st>>>(BALL_WQ_ARGS);

@@ -44,10 +44,10 @@ class PathReplay:
 
     def __init__(self, batch=8, n_points=24000, device="cuda", k=16, num_classes=13, ignore_index=None,
                  kind="surface", rank=0, first_scene=0, arch=XL, refine=False, refine_k=12, seed=0,
-                 with_grouping=True, with_loss=True, geometry_stream=True, prefetch=False):
+                 with_grouping=True, with_loss=True, geometry_stream=True, prefetch=False, loss_args=None):
         self.B, self.N, self.device = batch, n_points, torch.device(device)
         self.num_classes, self.ignore_index = num_classes, ignore_index
-        self.args = aa_args(k)
+        self.args = aa_args(k, **(loss_args or {}))      # e.g. ScanNet / MM: temperature=0.5, nu=0.6
         self.arch = arch
         self.refine, self.refine_k = refine, refine_k
         self.with_grouping, self.with_loss = with_grouping, with_loss

@@ -43,6 +43,17 @@ const char *amc3d_last_error(void);
  * No other global state: nothing here touches the device's default memory pool. */
 int amc3d_trim_scratch(size_t keep_bytes);
 
+/* Measurement hooks (bench.py; no caller on the product path).
+ * amc3d_fp32_probe launches `blocks` CTAs x 1024 threads of 8 independent FFMA chains of length `iters`
+ * and stores the FLOP it executes in *flop (host); timed by the caller -> measured FP32-pipe peak.
+ * `out` needs blocks*1024 floats (device; never written in practice).
+ * amc3d_search_stats registers a device array of 8 u64 counters (NULL = off, the default).  While
+ * registered, the culled searches launch counting instantiations of their kernels which add
+ * [0] kNN (warp per query) distance evaluations, [1] its queries, [2] kNN (thread per query) evaluations,
+ * [3] its queries, [4] ball-query evaluations, [5] its queries.  Results are unchanged. */
+int amc3d_fp32_probe(int iters, int blocks, float *out, double *flop, void *stream);
+int amc3d_search_stats(void *counters);
+
 /* ---------------------------------------------------------------------------------------
  * pointnet2_batch family: batched (B,N,3) xyz and (B,C,N) features, all contiguous f32/i32
  * ------------------------------------------------------------------------------------- */

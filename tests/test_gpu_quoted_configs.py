@@ -1,0 +1,222 @@
+"""Parity at the configurations the numbers are quoted on (BASELINE.json configs 2 and 3), and the drop-in
+proof on the reference's own Python.
+
+* config 2 — 8 x 24 000-point S3DIS-shaped scenes flattened into one segment (M_0 = 192 000), k = 16 and
+  k = 24 (the shipped yaml): the loss and all four grad f_s of `PathReplay` against the torch restatement of
+  the reference (oracle/loss_oracle.py) running on the SAME decoder features, with the reference's own kNN
+  kernel (oracle/_ref) underneath where it was built, bit-exact discrete intermediates.
+* config 3 — AMContrast3D++: 2 x 64 000 points, 20 classes + 5 % ignored labels, DualMasks (K = 8,
+  thr 0.9 / 1.0, gamma 0.4), T = 0.5, nu = 0.6: values, not finiteness.
+* the reference's ContrastHead / AmbiguityHead / QueryAndGroup / three_interpolation / furthest_point_sample
+  / pointops.knnquery, imported UNMODIFIED (oracle/ref_python.py) and running over
+  `amcontrast3d_b200.compat.install(tier=1)` — i.e. on this library's kernels through the extension-module
+  ABI — against this package's Tier-3 modules.
+
+Tolerances (BASELINE.json north_star): indices / labels / posmask / counts bit-exact; loss and gradients
+1e-5 relative; soft ambiguity values 2e-6 relative (pow ulps, see test_gpu_loss.py).
+"""
+import numpy as np
+import pytest
+import torch
+
+from _util import rel_err
+from oracle import loss_oracle as lo
+from oracle import ref_kernels as rk
+from oracle import ref_python as rp
+
+pytestmark = pytest.mark.gpu
+LOSS_RTOL = 1e-5
+GRAD_RTOL = 1e-5
+A_RTOL = 2e-6
+
+
+def _knn():
+    """the reference's own kNN kernel where oracle/_ref was built, else the oracle's torch brute force"""
+    return rk.knnquery if rk.available() else lo.knnquery
+
+
+def _check_a(a_gpu, a_ref):
+    a_gpu, a_ref = a_gpu.detach().cpu().numpy(), a_ref.detach().cpu().numpy()
+    assert np.array_equal(a_gpu == 0, a_ref == 0)
+    assert np.array_equal(a_gpu == 1, a_ref == 1)
+    assert np.allclose(a_gpu, a_ref, rtol=A_RTOL, atol=0)
+
+
+def _tie_free_rows(pts, offset, k):
+    """rows of the self-kNN whose k+1 nearest distances are pairwise distinct (the reference heap is
+    order-unstable under exactly equal distances) — from the reference search with k+1"""
+    _, d = _knn()(k + 1, pts, pts, offset, offset)
+    return (d[:, 1:] > d[:, :-1]).all(1)
+
+
+def _oracle_on(replay, feats, refine=False):
+    """oracle loss (+ DualMasks) on CUDA tensors over replay's points / labels and the given features"""
+    p = replay._fps_chain(replay.d_xyz)
+    f_in = [f.detach().clone().requires_grad_(True) for f in feats]
+    f_loss = f_in
+    if refine:
+        f_loss = []
+        for s in range(4):
+            B, n_s, D = replay.B, replay.n[s], replay.C[s]
+            f_bdn = f_in[s].view(B, n_s, D).transpose(1, 2).contiguous()
+            f_ref, _ = lo.dual_masks(p[s], f_bdn, replay._apm[s], replay.refine_k, "MIN", 1.0, 0.9, 0.4, knn=_knn())
+            f_loss.append(f_ref.transpose(1, 2).reshape(B * n_s, D))
+    sl = lo.make_stage_list([p[s].reshape(-1, 3).contiguous() for s in range(4)], f_loss)
+    loss, a_cat, a_list, inter = lo.contrast_head_forward(replay.d_labels.reshape(-1), sl, replay.num_classes,
+                                                          replay.ignore_index, replay.args, knn=_knn())
+    loss.backward()
+    return loss, a_cat, inter, [f.grad for f in f_in], p
+
+
+@pytest.mark.parametrize("k", [16, 24])
+def test_config2_loss_and_gradients_vs_oracle(k):
+    from amcontrast3d_b200.AMContrast3D.MarginContrast import _stage_ambiguity
+    from amcontrast3d_b200.AMContrast3D.AEF.utils import get_ftype
+    from amcontrast3d_b200 import _amloss
+    from amcontrast3d_b200.replay import PathReplay
+    r = PathReplay(batch=8, n_points=24000, k=k, with_grouping=False, prefetch=False)
+    loss = r.step()
+    torch.cuda.synchronize()
+    ref_loss, ref_a, inter, ref_g, p = _oracle_on(r, r.f_dec)
+    assert abs(loss.item() - ref_loss.item()) <= LOSS_RTOL * abs(ref_loss.item()), (loss.item(), ref_loss.item())
+    for s in range(4):
+        assert rel_err(r.f_dec[s].grad.cpu().numpy(), ref_g[s].cpu().numpy()) <= GRAD_RTOL, s
+    # discrete intermediates of every stage, bit-exact
+    sl = {"down": [{"p_out": p[s].reshape(-1, 3).contiguous(), "offset": r._offsets[s]} for s in range(4)]}
+    sl["up"] = sl["down"]
+    nstride = torch.tensor([4, 4, 4, 4])
+    sel_frac = []
+    for s in range(4):
+        st = _stage_ambiguity("up", s, sl, r.d_labels.reshape(-1), 13, None, r.args, nstride, get_ftype("latent")[0])
+        ref = inter[s]
+        assert torch.equal(st["cls"].long(), ref["cls"].long())
+        ok = _tie_free_rows(sl["up"][s]["p_out"], sl["up"][s]["offset"], k)
+        assert ok.float().mean() > 0.98
+        assert torch.equal(st["knn_idx"][ok], ref["knn_idx"][ok])
+        pm = _amloss.unpack_posmask(st["posbits"], st["nl"].ke)
+        assert torch.equal(pm[ok], ref["posmask"][ok])
+        assert torch.equal(st["cnt"].long()[ok], ref["posmask"].sum(-1)[ok])
+        _check_a(st["a"][ok], ref["a"][ok])
+        sel_frac.append(float(((ref["a"] > 0) & (ref["a"] <= 1)).float().mean()))
+    assert sel_frac[0] > 0.2          # the flattened, overlapping scenes make the boundary set large
+
+
+def test_config3_mm_loss_and_gradients_vs_oracle():
+    """BASELINE config 3: 2 x 64 000 points, 20 classes + ignore_index, DualMasks refinement before the loss"""
+    from amcontrast3d_b200.replay import PathReplay
+    r = PathReplay(batch=2, n_points=64000, k=16, num_classes=20, ignore_index=-100, refine=True, refine_k=8,
+                   with_grouping=False, prefetch=False, loss_args=dict(temperature=0.5, nu=0.6))
+    loss = r.step()
+    torch.cuda.synchronize()
+    ref_loss, ref_a, inter, ref_g, _ = _oracle_on(r, r.f_dec, refine=True)
+    assert abs(loss.item() - ref_loss.item()) <= LOSS_RTOL * abs(ref_loss.item()), (loss.item(), ref_loss.item())
+    for s in range(4):
+        g = r.f_dec[s].grad
+        assert torch.isfinite(g).all()
+        assert rel_err(g.cpu().numpy(), ref_g[s].cpu().numpy()) <= GRAD_RTOL, s
+    # the ignored labels became class 20 at stage 0
+    assert int(inter[0]["cls"].max()) == 20
+
+
+def test_config3_full_replay_runs_with_grouping():
+    """the same unit through the whole path (FPS 64 000 -> 16 000 -> ..., grouping, interpolation) — the values
+    of the loss are covered above; here: it runs, and the loss equals the loss-only replay's"""
+    from amcontrast3d_b200.replay import PathReplay
+    kw = dict(batch=2, n_points=64000, k=16, num_classes=20, ignore_index=-100, refine=True, refine_k=8,
+              prefetch=False, loss_args=dict(temperature=0.5, nu=0.6))
+    full = PathReplay(**kw)
+    only = PathReplay(with_grouping=False, **kw)
+    a, b = full.step().item(), only.step().item()
+    assert abs(a - b) <= 1e-6 * abs(b)
+    for t in full.F:
+        assert t.grad is not None and torch.isfinite(t.grad).all()
+
+
+# ------------------------------------------------------------------------------------------
+# the reference's own Python over the Tier-1 boundary
+# ------------------------------------------------------------------------------------------
+needs_ref = pytest.mark.skipif(not rp.available(), reason="reference Python neither at /root/reference nor staged")
+
+
+def _small_hierarchy(num_classes=13, ignore_fraction=0.0, n0=4096, batch=2, seed=3):
+    from amcontrast3d_b200 import scenes
+    from amcontrast3d_b200.layers import furthest_point_sample
+    xyz, lab = scenes.batch_of_scenes(batch, n0, "volume", first_scene=seed, num_classes=num_classes,
+                                      ignore_fraction=ignore_fraction)
+    p = [torch.from_numpy(xyz).cuda()]
+    for s in range(1, 4):
+        idx = furthest_point_sample(p[-1], p[-1].shape[1] // 4).long()
+        p.append(torch.gather(p[-1], 1, idx.unsqueeze(-1).expand(-1, -1, 3)).contiguous())
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    f = [torch.randn(batch * p[s].shape[1], 32 << s, device="cuda", generator=g) for s in range(4)]
+    return p, f, torch.from_numpy(lab.reshape(-1)).cuda()
+
+
+def _stage_list(p, f):
+    down = [{"p_out": p[s].reshape(-1, 3).contiguous(), "f_out": f[s].detach().clone().requires_grad_(True),
+             "offset": torch.tensor([p[s].shape[0] * p[s].shape[1]], dtype=torch.int32, device="cuda")} for s in range(4)]
+    return {"inputs": None, "down": down, "up": down}
+
+
+@needs_ref
+@pytest.mark.parametrize("ncls,ign,kw", [(13, None, {}), (20, -100, dict(temperature=0.5, nu=0.6, nsample=12))])
+def test_reference_contrast_head_over_tier1_matches_tier3(ncls, ign, kw):
+    """MarginContrast.py:262-273 of the reference, unmodified, on the sm_100a kNN through `pointops_cuda`
+    (compat tier 1) == this package's fused ContrastHead: the SURVEY §7.2 minimum slice."""
+    from amcontrast3d_b200.AMContrast3D import AmbiguityHead, ContrastHead
+    ref = rp.import_reference(1)
+    assert ref.MarginContrast.ContrastHead is not ContrastHead          # really the reference's class
+    d = dict(nsample=16, ccbeta=0.04, cctype="Method2", temperature=0.3, supervisedCL="Method1", db="-m",
+             margin="adaptive", mu=-1, nu=0.5, stages="up", stages_num=4, vis=False)
+    d.update(kw)
+    args = rp.Args(d)
+    p, f, target = _small_hierarchy(ncls, 0.05 if ign is not None else 0.0)
+    sl_ref, sl = _stage_list(p, f), _stage_list(p, f)
+    ref_loss, ref_a, ref_a_list = ref.MarginContrast.ContrastHead()(None, target, sl_ref, ncls, ign, args)
+    ref_loss.backward()
+    loss, a_cat, _ = ContrastHead()(None, target, sl, ncls, ign, args)
+    loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= LOSS_RTOL * abs(ref_loss.item()), (loss.item(), ref_loss.item())
+    _check_a(a_cat, ref_a)
+    for s in range(4):
+        assert rel_err(sl["up"][s]["f_out"].grad.cpu().numpy(), sl_ref["up"][s]["f_out"].grad.cpu().numpy()) <= GRAD_RTOL
+    a_head = ref.MarginContrast.AmbiguityHead()(target, sl_ref, ncls, ign, args)
+    ours = AmbiguityHead()(target, sl, ncls, ign, args)
+    for x, y in zip(ours, a_head):
+        _check_a(x, y)
+
+
+@needs_ref
+def test_reference_layers_over_tier1_match_tier2():
+    """group.py:235-255 QueryAndGroup, subsample.py:76-106, upsampling.py:92-102 and pointops.py:32-56 of the
+    reference running on this library through the two extension-module names == this package's operators."""
+    from amcontrast3d_b200 import layers, pointops
+    ref = rp.import_reference(1)
+    assert ref.group.QueryAndGroup is not layers.QueryAndGroup
+    p, _, _ = _small_hierarchy()
+    xyz, q_idx_src = p[0], p[1]
+    f = torch.randn(2, 64, xyz.shape[1], device="cuda")
+    # furthest_point_sample
+    i_ref = ref.subsample.furthest_point_sample(xyz, 1024)
+    i_our = layers.furthest_point_sample(xyz, 1024)
+    assert i_ref.dtype == i_our.dtype and torch.equal(i_ref, i_our)
+    # QueryAndGroup: dp (B,3,M,ns), fj (B,C,M,ns), forward and the gradient w.r.t. the features
+    f_ref, f_our = f.clone().requires_grad_(True), f.clone().requires_grad_(True)
+    dp_r, fj_r = ref.group.QueryAndGroup(0.2, 32, normalize_dp=True)(q_idx_src, xyz, f_ref)
+    dp_o, fj_o = layers.QueryAndGroup(0.2, 32, normalize_dp=True)(q_idx_src, xyz, f_our)
+    assert torch.equal(dp_r, dp_o) and torch.equal(fj_r, fj_o)
+    g = torch.randn_like(fj_r)
+    fj_r.backward(g)
+    fj_o.backward(g)
+    assert rel_err(f_our.grad.cpu().numpy(), f_ref.grad.cpu().numpy()) <= GRAD_RTOL
+    # three_interpolation
+    fc = torch.randn(2, 128, q_idx_src.shape[1], device="cuda")
+    up_r = ref.upsampling.three_interpolation(xyz, q_idx_src, fc)
+    up_o = layers.three_interpolation(xyz, q_idx_src, fc)
+    assert torch.equal(up_r, up_o)
+    # pointops.knnquery
+    flat = xyz.reshape(-1, 3).contiguous()
+    o = torch.tensor([flat.shape[0]], dtype=torch.int32, device="cuda")
+    ir, dr = ref.pointops.knnquery(16, flat, None, o, o)
+    io, do = pointops.knnquery(16, flat, None, o, o)
+    assert torch.equal(ir, io) and torch.equal(dr, do)
