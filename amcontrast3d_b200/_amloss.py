@@ -89,14 +89,40 @@ def posmask_count(nl: NeighbourList, cls):
     return posbits, cnt, max_cnt
 
 
+# Which torch backend's FP32 rounding of the reference's square_distance the ambiguity kernel reproduces
+# (amc3d.h, amc3d_ambiguity_backend): "cuda" — what the reference computes where it actually runs (its
+# ambiguity.py hard-codes .cuda()) — or "cpu" — what the reference's modules give when run on CPU, as for
+# tests/golden/loss_golden.npz.  Env AMC3D_AMBIGUITY_BACKEND sets the initial value.
+import os as _os
+AMBIGUITY_BACKEND = _os.environ.get("AMC3D_AMBIGUITY_BACKEND", "cuda")
+
+
+class ambiguity_backend:
+    """with ambiguity_backend("cpu"): ...   (tests against the CPU-generated golden vectors)"""
+
+    def __init__(self, name):
+        assert name in ("cpu", "cuda")
+        self.name = name
+
+    def __enter__(self):
+        global AMBIGUITY_BACKEND
+        self.prev, AMBIGUITY_BACKEND = AMBIGUITY_BACKEND, self.name
+
+    def __exit__(self, *exc):
+        global AMBIGUITY_BACKEND
+        AMBIGUITY_BACKEND = self.prev
+        return False
+
+
 def ambiguity(p, nl: NeighbourList, posbits, cnt, max_cnt, cctype: str, beta: float, nu: float):
     """-> (a (m) f32, stats (8) i32: [#selected, #boundary, 5 report bins, 0])"""
     assert p.is_contiguous() and p.dtype == torch.float32
     a = torch.empty((nl.m,), dtype=torch.float32, device=p.device)
     stats = torch.zeros((8,), dtype=torch.int32, device=p.device)
     with _capi.guard(p):
-        _capi.call("amc3d_ambiguity", nl.m, nl.ke, nl.ld, ptr(p), nl.ptr, ptr(posbits), ptr(cnt), ptr(max_cnt),
-                   _CCTYPE[cctype], float(beta), float(nu), ptr(a), ptr(stats), stream(p))
+        _capi.call("amc3d_ambiguity_backend", nl.m, nl.ke, nl.ld, ptr(p), nl.ptr, ptr(posbits), ptr(cnt), ptr(max_cnt),
+                   _CCTYPE[cctype], float(beta), float(nu), {"cpu": 0, "cuda": 1}[AMBIGUITY_BACKEND], ptr(a),
+                   ptr(stats), stream(p))
     return a, stats
 
 

@@ -76,6 +76,7 @@ SIGNATURES = {
     "amc3d_stage_labels": [_I, _I, _I, _I, _LL, _P, _P, _P, _P],
     "amc3d_posmask_count": [_I, _I, _I, _P, _P, _P, _P, _P, _P],
     "amc3d_ambiguity": [_I, _I, _I, _P, _P, _P, _P, _P, _I, _F, _F, _P, _P, _P],
+    "amc3d_ambiguity_backend": [_I, _I, _I, _P, _P, _P, _P, _P, _I, _F, _F, _I, _P, _P, _P],
     "amc3d_row_inv_norm": [_I, _I, _P, _P, _P],
     "amc3d_amloss_forward": [_I, _I, _I, _I, _P, _P, _P, _P, _P, POINTER(LossParams), _P, _P, _P],
     "amc3d_amloss_forward_order": [_I, _I, _I, _I, _P, _P, _P, _P, _P, POINTER(LossParams), _P, _P, _P, _P],
@@ -151,8 +152,8 @@ def _kernels_in(name: str, args) -> int:
         return 2 if args[-2] else 1            # transpose + interpolate
     if name in ("amc3d_three_interpolate_grad_ws", "amc3d_three_interpolate_grad_ws_set"):
         return 2 if args[-2] else 1            # scatter + transpose-accumulate (plus a memset)
-    if name == "amc3d_refine_backward":
-        return 2
+    if name in ("amc3d_refine_backward", "amc3d_ambiguity", "amc3d_ambiguity_backend"):
+        return 2                               # (boundary count + ambiguity)
     return 1
 
 

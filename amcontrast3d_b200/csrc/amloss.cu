@@ -86,20 +86,49 @@ posmask_count_kernel(int m, int ke, int ld, const int *__restrict__ nbr, const i
 // ---------------------------------------------------------------------------------------
 // ambiguity
 // ---------------------------------------------------------------------------------------
-// square_distance (AEF/function.py:36-38) for one pair, in the order torch evaluates it:
-//   dot  = ((x1*x2 + y1*y2) + z1*z2)      matmul over K=3, products and sums rounded separately
-//   dist = -2*dot ; dist += (x1^2+y1^2)+z1^2 ; dist += (x2^2+y2^2)+z2^2
-// (verified bit-for-bit against torch's CPU result of AEF/function.py square_distance)
-__device__ __forceinline__ float sqdist_torch(float x1, float y1, float z1, float n1, float x2,
+// square_distance (AEF/function.py:36-38) for one pair.  The expression |a|^2 + |b|^2 - 2ab is ill-conditioned
+// in FP32 for close points (d2 ~ 1e-4 from terms ~ 50), so its value — and through cc = n/d the ambiguity —
+// depends on the rounding order of the torch backend the reference happens to run on, and on CUDA even on the
+// number nb of boundary points, because cuBLAS switches kernels with the batch count of the
+// [nb,1,3] x [nb,3,k] product.  All variants are reproduced (V = variant):
+//   V 1,2: torch CUDA — what the reference computes where it actually runs; verified bit for bit against
+//          torch 2.11 / cuBLAS 12.8 on a B200 for nb = 1 ... 82 307, k = 4 ... 32 (tools/diag/probe*.py):
+//       V 1 (nb >= 153):  dot = fl(fma(y1,y2, fl(x1*x2)) + fl(z1*z2))
+//       V 2 (nb <  153):  dot = (fl(z1*z2) + fl(x1*x2)) + fl(y1*y2)
+//       |p|2 = (x*x + z*z) + y*y     (torch.sum(p ** 2, -1); x*x + (y*y + z*z) for the anchors when nb <= 2)
+//   V 0: torch CPU — what tests/golden/loss_golden.npz was generated with:
+//       dot  = (fl(x1*x2) + fl(y1*y2)) + fl(z1*z2) ;  |p|2 = (x*x + y*y) + z*z
+//   then, in all:  dist = -2*dot ; dist += |p1|2 ; dist += |p2|2
+__device__ __forceinline__ float sqnorm_torch(int v, float x, float y, float z) {
+    if (v == 0) return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+    if (v == 3) return __fadd_rn(__fmul_rn(x, x), __fadd_rn(__fmul_rn(y, y), __fmul_rn(z, z)));
+    return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(z, z)), __fmul_rn(y, y));
+}
+
+__device__ __forceinline__ float sqdist_torch(int v, float x1, float y1, float z1, float n1, float x2,
                                               float y2, float z2) {
-    const float dot = __fadd_rn(__fadd_rn(__fmul_rn(x1, x2), __fmul_rn(y1, y2)), __fmul_rn(z1, z2));
-    const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(x2, x2), __fmul_rn(y2, y2)), __fmul_rn(z2, z2));
+    float dot;
+    if (v == 1) dot = __fadd_rn(__fmaf_rn(y1, y2, __fmul_rn(x1, x2)), __fmul_rn(z1, z2));
+    else if (v == 2) dot = __fadd_rn(__fadd_rn(__fmul_rn(z1, z2), __fmul_rn(x1, x2)), __fmul_rn(y1, y2));
+    else dot = __fadd_rn(__fadd_rn(__fmul_rn(x1, x2), __fmul_rn(y1, y2)), __fmul_rn(z1, z2));
+    const float n2 = sqnorm_torch(v, x2, y2, z2);
     float d = __fmul_rn(-2.f, dot);
     d = __fadd_rn(d, n1);
     d = __fadd_rn(d, n2);
     return d;
 }
 
+// #boundary points (0 < cnt < max cnt) -> stats[1]; the ambiguity kernel needs the total before it starts
+__global__ void __launch_bounds__(256)
+boundary_count_kernel(int m, const int *__restrict__ cnt, const int *__restrict__ max_cnt, int *__restrict__ stats) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int mx = __ldg(max_cnt);
+    const int c = i < m ? __ldg(cnt + i) : 0;
+    const unsigned mb = __ballot_sync(0xffffffffu, c > 0 && c < mx);
+    if ((threadIdx.x & 31) == 0 && mb) atomicAdd(stats + 1, __popc(mb));
+}
+
+template <int BACKEND>
 __global__ void __launch_bounds__(256)
 ambiguity_kernel(int m, int ke, int ld, const float *__restrict__ p, const int *__restrict__ nbr,
                  const uint32_t *__restrict__ posbits, const int *__restrict__ cnt,
@@ -108,6 +137,13 @@ ambiguity_kernel(int m, int ke, int ld, const float *__restrict__ p, const int *
     const int i = blockIdx.x * 256 + threadIdx.x;
     bool sel = false, boundary = false;
     int bin = -1;
+    // the rounding variant (see sqdist_torch): uniform over the grid
+    int v = 0, v1 = 0;
+    if (BACKEND == 1) {
+        const int nb = stats[1];
+        v = nb >= 153 ? 1 : 2;
+        v1 = nb <= 2 ? 3 : v;
+    }
     if (i < m) {
         const int mx = __ldg(max_cnt);
         const int c = __ldg(cnt + i);
@@ -121,12 +157,12 @@ ambiguity_kernel(int m, int ke, int ld, const float *__restrict__ p, const int *
             } else {
                 const uint32_t bits = __ldg(posbits + i);
                 const float x1 = __ldg(p + 3ll * i), y1 = __ldg(p + 3ll * i + 1), z1 = __ldg(p + 3ll * i + 2);
-                const float n1 = __fadd_rn(__fadd_rn(__fmul_rn(x1, x1), __fmul_rn(y1, y1)), __fmul_rn(z1, z1));
+                const float n1 = sqnorm_torch(v1, x1, y1, z1);
                 const int *row = nbr + (long long)i * ld;
                 dpos = 0.f; dneg = 0.f;
                 for (int j = 0; j < ke; ++j) {
                     const long long nj = __ldg(row + j);
-                    float dd = sqdist_torch(x1, y1, z1, n1, __ldg(p + 3 * nj), __ldg(p + 3 * nj + 1),
+                    float dd = sqdist_torch(v, x1, y1, z1, n1, __ldg(p + 3 * nj), __ldg(p + 3 * nj + 1),
                                             __ldg(p + 3 * nj + 2));
                     if (cctype == 3) dd = __fsqrt_rn(__fadd_rn(fabsf(dd), 1e-12f));
                     if ((bits >> j) & 1u) dpos = __fadd_rn(dpos, dd);
@@ -150,13 +186,11 @@ ambiguity_kernel(int m, int ke, int ld, const float *__restrict__ p, const int *
     }
     // warp-aggregated counters
     const unsigned ms = __ballot_sync(0xffffffffu, sel);
-    const unsigned mb = __ballot_sync(0xffffffffu, boundary);
     unsigned mbin[5];
 #pragma unroll
     for (int t = 0; t < 5; ++t) mbin[t] = __ballot_sync(0xffffffffu, bin == t);
     if ((threadIdx.x & 31) == 0) {
         if (ms) atomicAdd(stats + 0, __popc(ms));
-        if (mb) atomicAdd(stats + 1, __popc(mb));
 #pragma unroll
         for (int t = 0; t < 5; ++t)
             if (mbin[t]) atomicAdd(stats + 2 + t, __popc(mbin[t]));
@@ -550,13 +584,26 @@ extern "C" int amc3d_posmask_count(int m, int ke, int ld, const int *nbr, const 
 extern "C" int amc3d_ambiguity(int m, int ke, int ld, const float *p, const int *nbr, const uint32_t *posbits,
                                const int *cnt, const int *max_cnt, int cctype, float beta, float nu,
                                float *a, int *stats, void *stream) {
+    return amc3d_ambiguity_backend(m, ke, ld, p, nbr, posbits, cnt, max_cnt, cctype, beta, nu, 1, a, stats, stream);
+}
+
+extern "C" int amc3d_ambiguity_backend(int m, int ke, int ld, const float *p, const int *nbr,
+                                       const uint32_t *posbits, const int *cnt, const int *max_cnt, int cctype,
+                                       float beta, float nu, int torch_backend, float *a, int *stats,
+                                       void *stream) {
+    AMC3D_REQUIRE(torch_backend == 0 || torch_backend == 1, AMC3D_EINVAL, "ambiguity: torch_backend=%d not 0 (cpu) / 1 (cuda)", torch_backend);
     AMC3D_REQUIRE(m >= 0 && ke >= 1 && ke <= KE_MAX && ld >= ke, AMC3D_EINVAL, "ambiguity: bad sizes m=%d ke=%d ld=%d", m, ke, ld);
     AMC3D_REQUIRE(cctype >= 1 && cctype <= 3, AMC3D_EINVAL, "ambiguity: cctype=%d not in 1..3", cctype);
     if (m == 0) return 0;
     // nu_m = nu * 10 in Python double, compared against float32 tensors (ambiguity.py:77)
     const float nu_m = (float)((double)nu * 10.0);
-    ambiguity_kernel<<<div_up(m, 256), 256, 0, as_stream(stream)>>>(m, ke, ld, p, nbr, posbits, cnt, max_cnt,
-                                                                     cctype, beta, nu_m, a, stats);
+    boundary_count_kernel<<<div_up(m, 256), 256, 0, as_stream(stream)>>>(m, cnt, max_cnt, stats);
+    if (torch_backend == 1)
+        ambiguity_kernel<1><<<div_up(m, 256), 256, 0, as_stream(stream)>>>(m, ke, ld, p, nbr, posbits, cnt, max_cnt,
+                                                                            cctype, beta, nu_m, a, stats);
+    else
+        ambiguity_kernel<0><<<div_up(m, 256), 256, 0, as_stream(stream)>>>(m, ke, ld, p, nbr, posbits, cnt, max_cnt,
+                                                                            cctype, beta, nu_m, a, stats);
     return check_launch("ambiguity");
 }
 

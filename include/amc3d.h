@@ -269,6 +269,16 @@ int amc3d_posmask_count(int m, int ke, int ld, const int *nbr, const int *cls, u
 int amc3d_ambiguity(int m, int ke, int ld, const float *p, const int *nbr, const uint32_t *posbits,
                     const int *cnt, const int *max_cnt, int cctype, float beta, float nu,
                     float *a, int *stats, void *stream);
+/* Same with the torch backend whose FP32 rounding of square_distance is reproduced: the reference's
+ * |a|^2 + |b|^2 - 2ab is ill-conditioned for close points, and torch's CPU (sgemm, (x+y)+z) and CUDA
+ * (cuBLAS fma(y,y',xx') + zz', (x+z)+y) kernels round it differently, so the reference's own `a` differs
+ * between its CPU and CUDA runs (up to 3e-2 at BASELINE config 2).  torch_backend 1 = CUDA (what the
+ * reference computes where it runs; amc3d_ambiguity uses it; cuBLAS switches kernels at 153 boundary
+ * points, which is followed), 0 = CPU (what the golden vectors hold).  Two launches: a boundary count
+ * into stats[1], then the ambiguity kernel. */
+int amc3d_ambiguity_backend(int m, int ke, int ld, const float *p, const int *nbr,
+                            const uint32_t *posbits, const int *cnt, const int *max_cnt, int cctype,
+                            float beta, float nu, int torch_backend, float *a, int *stats, void *stream);
 
 /* inv[i] = 1 / max(||f_i||_2, 1e-8).  f (m,d) row-major. */
 int amc3d_row_inv_norm(int m, int d, const float *f, float *inv, void *stream);

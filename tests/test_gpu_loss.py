@@ -15,6 +15,16 @@ from _util import GOLDEN_CASES, build_hierarchy, rel_err, stage_list_of
 from oracle import loss_oracle as lo
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _cpu_rounding_of_square_distance():
+    """Everything here is compared with results the reference / the oracle produced on CPU, so the ambiguity
+    kernel reproduces torch's CPU rounding of square_distance (amc3d.h, amc3d_ambiguity_backend); the CUDA
+    rounding — the default — is covered by tests/test_gpu_quoted_configs.py against torch on the GPU."""
+    from amcontrast3d_b200 import _amloss
+    with _amloss.ambiguity_backend("cpu"):
+        yield
 DEV = "cuda"
 A_RTOL = 2e-6      # soft ambiguity values (pow ulps)
 LOSS_RTOL = 1e-5   # north_star tolerance for the loss

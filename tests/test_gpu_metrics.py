@@ -18,6 +18,16 @@ sys.path.insert(0, os.path.join(REPO, "tests", "golden"))
 DEV = "cuda"
 
 
+@pytest.fixture(autouse=True)
+def _cpu_rounding_of_square_distance():
+    """The golden file holds the reference's metrics.py run on CPU: reproduce torch's CPU rounding of
+    square_distance (amc3d.h, amc3d_ambiguity_backend); the default CUDA rounding is covered by
+    tests/test_gpu_quoted_configs.py against torch on the GPU."""
+    from amcontrast3d_b200 import _amloss
+    with _amloss.ambiguity_backend("cpu"):
+        yield
+
+
 class _ConfusionMatrix:
     """Test double with the interface ambiguity_metrics uses of openpoints/utils/metrics.py:51-142
     (update / tp / union / count), written from its documented behaviour."""
