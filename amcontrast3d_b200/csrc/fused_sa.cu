@@ -1,0 +1,885 @@
+// Fused  grouping -> 1x1 conv -> BatchNorm (training statistics) -> ReLU -> max over the neighbourhood
+// (SURVEY.md §8f rank 1): the operator PointNeXt's SetAbstraction / LocalAggregation compose from
+// QueryAndGroup + Conv2d + BatchNorm2d + ReLU + max  (ref: openpoints/models/backbone/pointnext_AA.py:57-63,
+// :139-170; grouper openpoints/models/layers/group.py:235-255).  The grouped tensor (B, 3+C, M, ns) — 6.45 GB
+// written and re-read per step at BASELINE config 2 — is never materialised.
+//
+//   forward    y[o, p] = sum_k W'[o, k] x[p, k]        x[p] = [ f[b, idx[p], 0..C) | (xyz[idx[p]] - q) / r | 0 ]
+//              as tcgen05 MMAs (kind::tf32, FP32 accumulators in TMEM):  M = 128 output channels, N = 128 grouped
+//              positions (= 128 / ns queries), K = C + 8 in 128-byte chunks.  The B operand (positions x K) is
+//              GATHERED: 8 lanes fetch one neighbour's 128 contiguous bytes of the channel-contiguous (B, N, C)
+//              feature copy and store them into the 128B-swizzled K-major tile the MMA reads; the A operand (W')
+//              is staged the same way.  The epilogue thread that owns TMEM lane o holds the ns conv outputs of a
+//              query in registers, so max / arg-max over the neighbourhood and the BatchNorm sums are
+//              thread-local.  BatchNorm + ReLU are monotone in y (increasing for gamma >= 0, decreasing
+//              otherwise), hence  max_s relu(bn(y_s)) = relu(bn(max_s y_s))  (min for gamma < 0): ONE pass over
+//              the gathered rows gives the pre-normalisation extreme per (query, channel) and the statistics;
+//              a small second kernel normalises.
+//   precision  X3 = false: operands are read as TF32 by the tensor core (what the reference's cuDNN convolution
+//              does on Ampere and later: torch.backends.cudnn.allow_tf32 defaults to True);
+//              X3 = true: error-compensated 3 x TF32 (hi*hi + lo*hi + hi*lo, hi = rna(x), lo = x - hi), FP32-faithful
+//              to ~1e-6 — what the CPU-generated golden vectors are held to (2e-5).
+#include "common.cuh"
+#include <stdlib.h>
+#include <type_traits>
+
+namespace amc3d {
+
+constexpr int FS_NT = 128;                 // grouped positions per CTA (UMMA N)
+constexpr int FS_ROWB = 128;               // bytes per tile row = one swizzle span = 32 floats of K
+constexpr int FS_PROD = 128;               // producer / epilogue threads (warps 0-3); warp 4 issues the MMAs
+constexpr int FS_THREADS = FS_PROD + 32;
+constexpr int FS_MAX_STAGES = 4;
+constexpr int FS_REPL = 64;                // replicas of the BatchNorm sums (spreads the atomics over 64x the cache lines)
+
+__device__ __forceinline__ uint32_t fs_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], 128 x N x 8 (TF32), issued by one thread for the CTA
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// arrive on an mbarrier once every MMA issued so far has completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// K-major operand tile, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), tile base
+// 1024-byte aligned; advancing along K inside the swizzle span = adding bytes to the start address.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;                  // leading byte offset (unused for swizzled K-major), 16 B
+    d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                  // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, M x N
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// 16-byte slot `c` (0..7) of row `r` inside a 128B-swizzled tile
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) { return (uint32_t)(r * FS_ROWB + ((c ^ (r & 7)) << 4)); }
+
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+// 16-byte asynchronous global -> shared copy (LDGSTS); `valid` false writes zeros without reading
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool valid) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16u : 0u) : "memory");
+}
+
+template <bool X3>
+__device__ __forceinline__ void fs_store(unsigned char *hi, unsigned char *lo, uint32_t off, float4 v) {
+    if (X3) {
+        float4 h = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+        *reinterpret_cast<float4 *>(hi + off) = h;
+        *reinterpret_cast<float4 *>(lo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+    } else {
+        *reinterpret_cast<float4 *>(hi + off) = v;
+    }
+}
+
+template <int NS>
+__device__ __forceinline__ void tmem_ld_query(uint32_t taddr, float (&v)[NS]);
+
+template <>
+__device__ __forceinline__ void tmem_ld_query<32>(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <>
+__device__ __forceinline__ void tmem_ld_query<16>(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct FusedFwdArgs {
+    const float *fT;        // (B, N, C) channel-contiguous features
+    const float *xyz;       // (B, N, 3) support points
+    const float *qxyz;      // (B, M, 3) query points
+    const int *idx;         // (B, M, NS)
+    const float *Wp;        // (O, Kp): [W[:, 3:3+C] | W[:, 0:3] | 0]
+    const float *gamma;     // (O) BatchNorm weight: its sign selects max or min
+    float *ysel;            // (B*M, O) pre-normalisation extreme of y over the neighbourhood
+    unsigned char *arg;     // (B*M, O) sample index of that extreme (first one)
+    double *gsum, *gsumsq;  // (O) sum y, sum y^2 over all B*M*NS positions (zeroed by the caller)
+    int B, N, M, C, O, Kp, oc, stages;
+    float inv_radius;       // 1/radius with normalize_dp, else 1
+};
+
+template <int NS, bool X3>
+__global__ void __launch_bounds__(FS_THREADS, 3)
+fused_sa_fwd_kernel(const FusedFwdArgs a) {
+    constexpr int QPT = FS_NT / NS;                       // queries per tile
+    extern __shared__ __align__(1024) unsigned char fs_smem_raw[];
+    // the runtime only guarantees 16-byte alignment of dynamic shared memory: align by hand
+    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(fs_smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int oc = a.oc;                                  // output channels of this CTA (128 / 256 / 512)
+    const uint32_t x_bytes = FS_NT * FS_ROWB, w_bytes = (uint32_t)oc * FS_ROWB;
+    const uint32_t stage_bytes = (X3 ? 2u : 1u) * (x_bytes + w_bytes);
+    __shared__ __align__(8) uint64_t bars[2 * FS_MAX_STAGES + 1];
+    const int FS_STAGES = a.stages;
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const long long Q = (long long)a.B * a.M;
+    const long long q0 = (long long)blockIdx.x * QPT;
+    const int o0 = blockIdx.y * oc;
+    const int nchunks = (a.Kp + 31) / 32;
+
+    if (tid == 0) {
+        for (int s = 0; s < FS_STAGES; ++s) {
+            mbar_init(fs_smem(&bars[s]), FS_PROD);                 // full[s]: every producer thread arrives
+            mbar_init(fs_smem(&bars[FS_STAGES + s]), 1);           // empty[s]: one tcgen05.commit
+        }
+        mbar_init(fs_smem(&bars[2 * FS_STAGES]), 1);               // accumulators complete
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {                                               // TMEM: oc columns (128 lanes x oc x f32)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(fs_smem(&tmem_base_s)),
+                     "r"((uint32_t)oc)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp < 4) {
+        // ------------------------------------------------------------------ producers
+        const int slot = tid & 7, rsub = tid >> 3;                 // 8 lanes per 128-byte row, 16 rows per pass
+        // the 8 grouped positions this thread fetches: row r = i*16 + rsub -> (query, sample) -> support row
+        long long frow[FS_NT / 16];                                // (b*N + n) * C, or -1 past the end
+        int qof[FS_NT / 16];                                       // query index (for the relative coordinates)
+#pragma unroll
+        for (int i = 0; i < FS_NT / 16; ++i) {
+            const int r = i * 16 + rsub;
+            const long long qg = q0 + r / NS;
+            frow[i] = -1;
+            qof[i] = 0;
+            if (qg < Q) {
+                const int n = __ldg(a.idx + qg * NS + (r % NS));
+                const long long b = qg / a.M;
+                frow[i] = (b * a.N + n);
+                qof[i] = (int)(qg - q0);
+            }
+        }
+        // fill stage `st` with K chunk `kc`.  ASYNC (TF32 mode): 16-byte cp.async copies straight into the swizzled
+        // tile — no registers, so several chunks are in flight per thread; otherwise through registers (the 3xTF32
+        // split needs the values).
+        auto fill = [&](int kc, auto async_tag) {
+            constexpr bool ASYNC = decltype(async_tag)::value;
+            const int st = kc % FS_STAGES;
+            if (kc >= FS_STAGES) mbar_wait(fs_smem(&bars[FS_STAGES + st]), (uint32_t)((kc / FS_STAGES - 1) & 1));
+            unsigned char *xs = base + (size_t)st * stage_bytes;
+            unsigned char *xl = xs + x_bytes;                      // X3 only
+            unsigned char *ws = xs + (X3 ? 2u : 1u) * x_bytes;
+            unsigned char *wl = ws + w_bytes;                      // X3 only
+            const int k0 = kc * 32 + slot * 4;
+            // X: gathered neighbour rows | relative coordinates | zeros
+#pragma unroll
+            for (int i = 0; i < FS_NT / 16; ++i) {
+                const int r = i * 16 + rsub;
+                const bool feat = frow[i] >= 0 && k0 + 4 <= a.C;
+                if (ASYNC && !(frow[i] >= 0 && k0 == a.C)) {
+                    cp_async16(fs_smem(xs) + sw128_off(r, slot), feat ? a.fT + frow[i] * a.C + k0 : a.fT, feat);
+                    continue;
+                }
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (feat) {
+                    v = __ldg(reinterpret_cast<const float4 *>(a.fT + frow[i] * a.C + k0));
+                } else if (frow[i] >= 0 && k0 == a.C) {
+                    const float *pp = a.xyz + frow[i] * 3;
+                    const float *qq = a.qxyz + (q0 + qof[i]) * 3;
+                    v.x = (__ldg(pp) - __ldg(qq)) * a.inv_radius;
+                    v.y = (__ldg(pp + 1) - __ldg(qq + 1)) * a.inv_radius;
+                    v.z = (__ldg(pp + 2) - __ldg(qq + 2)) * a.inv_radius;
+                }
+                fs_store<X3>(xs, xl, sw128_off(r, slot), v);
+            }
+            // W': rows o0 .. o0+oc
+            for (int i = 0; i < oc / 16; ++i) {
+                const int r = i * 16 + rsub;
+                const int o = o0 + r;
+                const bool ok = o < a.O && k0 < a.Kp;
+                if (ASYNC) {
+                    cp_async16(fs_smem(ws) + sw128_off(r, slot), ok ? a.Wp + (long long)o * a.Kp + k0 : a.Wp, ok);
+                } else {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok) v = __ldg(reinterpret_cast<const float4 *>(a.Wp + (long long)o * a.Kp + k0));
+                    fs_store<X3>(ws, wl, sw128_off(r, slot), v);
+                }
+            }
+        };
+        if (!X3) {
+            // software pipeline: the copies of chunk kc + STAGES - 1 are issued before chunk kc is handed to the MMA
+            for (int kc = 0; kc < FS_STAGES - 1; ++kc) {
+                if (kc < nchunks) fill(kc, std::true_type{});
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
+            for (int kc = 0; kc < nchunks; ++kc) {
+                if (kc + FS_STAGES - 1 < nchunks) fill(kc + FS_STAGES - 1, std::true_type{});
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                // all but the newest STAGES-1 groups are complete -> chunk kc has landed (this thread's part)
+                if (FS_STAGES == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+                else if (FS_STAGES == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+                else asm volatile("cp.async.wait_group 3;" ::: "memory");
+                fence_async_smem();                                // generic-proxy writes -> visible to the MMA (async proxy)
+                mbar_arrive(fs_smem(&bars[kc % FS_STAGES]));
+            }
+        } else {
+            for (int kc = 0; kc < nchunks; ++kc) {
+                fill(kc, std::false_type{});
+                fence_async_smem();
+                mbar_arrive(fs_smem(&bars[kc % FS_STAGES]));
+            }
+        }
+
+        // ------------------------------------------------------------------ epilogue: this thread owns channel lane `tid`
+        mbar_wait(fs_smem(&bars[2 * FS_STAGES]), 0);
+        tc_fence_after();
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int j = 0; j < oc / 128; ++j) {
+            const int o = o0 + j * 128 + tid;
+            const bool live = o < a.O;
+            const bool want_max = live ? (__ldg(a.gamma + o) >= 0.f) : true;
+            float csum = 0.f, csq = 0.f;
+#pragma unroll 1
+            for (int qi = 0; qi < QPT; ++qi) {
+                float v[NS];
+                __syncwarp();                                      // .sync.aligned: reconverge after the `continue` below
+                tmem_ld_query<NS>(lane_addr + (uint32_t)(j * 128 + qi * NS), v);    // all lanes of the warp take part
+                const long long qg = q0 + qi;
+                if (!live || qg >= Q) continue;
+                float best = v[0];
+                int bi = 0;
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    s1 += v[s];
+                    s2 = fmaf(v[s], v[s], s2);
+                    const bool better = want_max ? (v[s] > best) : (v[s] < best);
+                    if (better) { best = v[s]; bi = s; }
+                }
+                csum += s1;
+                csq += s2;
+                a.ysel[qg * a.O + o] = best;
+                a.arg[qg * a.O + o] = (unsigned char)bi;
+            }
+            if (live) {
+                const long long rep = (long long)(blockIdx.x % FS_REPL) * 2 * a.O;
+                atomicAdd(a.gsum + rep + o, (double)csum);
+                atomicAdd(a.gsumsq + rep + o, (double)csq);
+            }
+        }
+        tc_fence_before();
+    } else {
+        // ------------------------------------------------------------------ MMA issuer (one elected lane)
+        const uint32_t idesc = umma_idesc_tf32(128, FS_NT);
+        for (int kc = 0; kc < nchunks; ++kc) {
+            const int st = kc % FS_STAGES;
+            mbar_wait(fs_smem(&bars[st]), (uint32_t)((kc / FS_STAGES) & 1));
+            tc_fence_after();
+            if ((tid & 31) == 0) {
+                const uint32_t xs = fs_smem(base + (size_t)st * stage_bytes);
+                const uint32_t xl = xs + x_bytes;
+                const uint32_t ws = xs + (X3 ? 2u : 1u) * x_bytes;
+                const uint32_t wl = ws + w_bytes;
+                const int ksteps = min(4, (a.Kp - kc * 32) / 8);
+                for (int j = 0; j < oc / 128; ++j) {
+                    const uint32_t d = tmem_base + (uint32_t)(j * 128);
+                    const uint32_t wrow = (uint32_t)(j * 128 * FS_ROWB);
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint32_t first = (kc > 0 || ks > 0) ? 1u : 0u;
+                        const uint64_t da = umma_desc_sw128(ws + wrow + ks * 32), db = umma_desc_sw128(xs + ks * 32);
+                        if (X3) {
+                            umma_tf32(d, umma_desc_sw128(wl + wrow + ks * 32), db, idesc, first);   // lo * hi
+                            umma_tf32(d, da, umma_desc_sw128(xl + ks * 32), idesc, 1u);             // hi * lo
+                            umma_tf32(d, da, db, idesc, 1u);                                         // hi * hi
+                        } else {
+                            umma_tf32(d, da, db, idesc, first);
+                        }
+                    }
+                }
+                umma_commit(fs_smem(&bars[FS_STAGES + st]));        // frees the stage once these MMAs have read it
+                if (kc == nchunks - 1) umma_commit(fs_smem(&bars[2 * FS_STAGES]));
+            }
+            __syncwarp();
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)oc) : "memory");
+    }
+}
+
+// BatchNorm statistics from the sums: mean, biased variance, 1/sqrt(var + eps)
+__global__ void fused_sa_stats_kernel(int O, double count, float eps, const double *__restrict__ gsum,
+                                      const double *__restrict__ gsumsq, float *__restrict__ mean,
+                                      float *__restrict__ var, float *__restrict__ invstd) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= O) return;
+    double s1 = 0.0, s2 = 0.0;
+    for (int r = 0; r < FS_REPL; ++r) {
+        s1 += gsum[(long long)r * 2 * O + o];
+        s2 += gsumsq[(long long)r * 2 * O + o];
+    }
+    const double m = s1 / count;
+    double v = s2 / count - m * m;
+    if (v < 0.0) v = 0.0;
+    mean[o] = (float)m;
+    var[o] = (float)v;
+    invstd[o] = (float)(1.0 / sqrt(v + (double)eps));
+}
+
+// out[b, o, m] = relu((ysel[b*M + m, o] - mean[o]) * invstd[o] * gamma[o] + beta[o]); 32 x 32 transposing tiles
+__global__ void __launch_bounds__(256)
+fused_sa_finalize_kernel(int B, int M, int O, const float *__restrict__ ysel, const float *__restrict__ mean,
+                         const float *__restrict__ invstd, const float *__restrict__ gamma,
+                         const float *__restrict__ beta, float *__restrict__ out) {
+    __shared__ float t[32][33];
+    const int b = blockIdx.z, m0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty + 8 * i, o = o0 + tx;
+        float v = 0.f;
+        if (m < M && o < O) {
+            const float y = __ldg(ysel + ((long long)b * M + m) * O + o);
+            v = fmaxf((y - __ldg(mean + o)) * __ldg(invstd + o) * __ldg(gamma + o) + __ldg(beta + o), 0.f);
+        }
+        t[ty + 8 * i][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int o = o0 + ty + 8 * i, m = m0 + tx;
+        if (m < M && o < O) out[((long long)b * O + o) * M + m] = t[tx][ty + 8 * i];
+    }
+}
+
+template <int NS, bool X3>
+static int launch_fused_fwd(const FusedFwdArgs &a, cudaStream_t st) {
+    const size_t smem = (size_t)a.stages * (X3 ? 2 : 1) * (FS_NT * FS_ROWB + (size_t)a.oc * FS_ROWB) + 1024;
+    cudaError_t e = cudaFuncSetAttribute(fused_sa_fwd_kernel<NS, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    // several CTAs per SM (the epilogue of one overlaps the main loop of another): ask for the full shared-memory carve-out
+    e = cudaFuncSetAttribute(fused_sa_fwd_kernel<NS, X3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
+    const long long Q = (long long)a.B * a.M;
+    dim3 grid((unsigned)div_up_ll(Q, FS_NT / NS), (unsigned)div_up(a.O, a.oc));
+    fused_sa_fwd_kernel<NS, X3><<<grid, FS_THREADS, smem, st>>>(a);
+    return 0;
+}
+
+}  // namespace amc3d
+
+using namespace amc3d;
+
+extern "C" int amc3d_fused_sa_forward(int b, int n, int m, int c, int o, int nsample, float radius, int normalize_dp,
+                                      int precision, float eps, const float *featT, const float *xyz,
+                                      const float *new_xyz, const int *idx, const float *w_packed,
+                                      const float *gamma, const float *beta, float *ysel, unsigned char *arg,
+                                      double *sums, float *mean, float *var, float *invstd, float *out,
+                                      void *stream) {
+    AMC3D_REQUIRE(b >= 0 && n >= 1 && m >= 0 && c >= 8 && o >= 1, AMC3D_EINVAL, "fused_sa_forward: bad sizes b=%d n=%d m=%d c=%d o=%d", b, n, m, c, o);
+    AMC3D_REQUIRE(c % 8 == 0, AMC3D_ELIMIT, "fused_sa_forward: C=%d is not a multiple of 8", c);
+    AMC3D_REQUIRE(nsample == 16 || nsample == 32, AMC3D_ELIMIT, "fused_sa_forward: nsample=%d (16 and 32 are built)", nsample);
+    AMC3D_REQUIRE(precision == 1 || precision == 3, AMC3D_EINVAL, "fused_sa_forward: precision=%d is not 1 (TF32) / 3 (3xTF32)", precision);
+    AMC3D_REQUIRE(b <= 65535, AMC3D_ELIMIT, "fused_sa_forward: batch %d > 65535", b);
+    if (b == 0 || m == 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    FusedFwdArgs a;
+    a.fT = featT; a.xyz = xyz; a.qxyz = new_xyz; a.idx = idx; a.Wp = w_packed; a.gamma = gamma;
+    a.ysel = ysel; a.arg = arg; a.gsum = sums; a.gsumsq = sums + o;
+    a.B = b; a.N = n; a.M = m; a.C = c; a.O = o; a.Kp = c + 8;
+    a.inv_radius = normalize_dp ? 1.0f / radius : 1.0f;
+    const int opad = div_up(o, 128) * 128;
+    // output channels per CTA (TMEM columns) and pipeline depth: tunable for measurements
+    static const int env_oc = getenv("AMC3D_FUSED_OC") ? atoi(getenv("AMC3D_FUSED_OC")) : 0;
+    static const int env_st = getenv("AMC3D_FUSED_STAGES") ? atoi(getenv("AMC3D_FUSED_STAGES")) : 0;
+    const int ocmax = precision == 3 ? 256 : 512;                   // shared-memory budget of a stage
+    a.oc = opad <= 128 ? 128 : (opad <= 256 || ocmax == 256 ? 256 : 512);
+    if (env_oc == 128 || env_oc == 256 || (env_oc == 512 && ocmax == 512)) a.oc = min(env_oc, a.oc);
+    a.stages = 2;
+    if (env_st >= 2 && env_st <= FS_MAX_STAGES) a.stages = env_st;
+    while (a.stages > 2 && (size_t)a.stages * (precision == 3 ? 2 : 1) * (FS_NT * FS_ROWB + (size_t)a.oc * FS_ROWB) + 2048 > 227 * 1024) --a.stages;
+    cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)o * FS_REPL, st);
+    int rc;
+    if (nsample == 32) rc = precision == 3 ? launch_fused_fwd<32, true>(a, st) : launch_fused_fwd<32, false>(a, st);
+    else rc = precision == 3 ? launch_fused_fwd<16, true>(a, st) : launch_fused_fwd<16, false>(a, st);
+    if (rc != 0) {
+        set_error("fused_sa_forward: %s", cudaGetErrorString((cudaError_t)rc));
+        return rc;
+    }
+    const double count = (double)b * m * nsample;
+    fused_sa_stats_kernel<<<div_up(o, 128), 128, 0, st>>>(o, count, eps, sums, sums + o, mean, var, invstd);
+    dim3 fgrid(div_up(m, 32), div_up(o, 32), b);
+    fused_sa_finalize_kernel<<<fgrid, 256, 0, st>>>(b, m, o, ysel, mean, invstd, gamma, beta, out);
+    return check_launch("fused_sa_forward");
+}
+
+namespace amc3d {
+
+// =================================================================================================================
+// Backward.  With  yhat = (y - mean) * invstd,  z = gamma * yhat + beta,  out = max_s relu(z)  and  G = dL/dout:
+//   D[p,o]  = G[q,o] * [out > 0] * [s(p) == arg(q,o)]                (one non-zero per (query, channel))
+//   dbeta   = sum_p D            dgamma = sum_p D * yhat
+//   dL/dy[p,o] = ghat_o * D[p,o] - c0_o - c1_o * y[p,o]     ghat = gamma*invstd, c1 = ghat*invstd*dgamma/P,
+//                                                           c0 = ghat*dbeta/P - c1*mean
+// The two terms without D are DENSE over all P positions but linear in x, so they reduce to the first and second
+// moments of the grouped input (sum_p x, sum_p x x^T), which in turn reduce to per-support-point counts because
+// x[p] = [f[idx[p]] | dp[p]]:  sum_p f[idx[p]] f[idx[p]]^T = sum_n cnt[n] f[n] f[n]^T — plain (B*N) x C x C GEMMs, 1/ns
+// of the convolution's work, done by the host side with library GEMMs.  The D terms are SPARSE (1/ns dense):
+//   dW[o,:]  += ghat_o * sum_q G'[q,o] * x[p*(q,o), :]                    fused_sa_bwd_dw_kernel  (CUDA cores)
+//   dx[p,:]  += sum_o ghat_o * D[p,o] * W[o,:]   -> scatter-add to df      fused_sa_bwd_dx_kernel  (tcgen05)
+// Nothing of size P x (3+C) or P x O is ever stored.
+// =================================================================================================================
+
+// gy[q,o] = G[b,o,m] * [out[b,o,m] > 0] * gamma[o] * invstd[o]   ((B,O,M) -> (B*M,O));  dbeta, dgamma (f64, atomics)
+__global__ void __launch_bounds__(256)
+fused_sa_bwd_prep_kernel(int B, int M, int O, const float *__restrict__ gout, const float *__restrict__ out,
+                         const float *__restrict__ ysel, const float *__restrict__ mean,
+                         const float *__restrict__ invstd, const float *__restrict__ gamma, float *__restrict__ gy,
+                         double *__restrict__ dbeta, double *__restrict__ dgamma) {
+    __shared__ float t[32][33];
+    __shared__ float rb[8][32], rg[8][32];
+    const int b = blockIdx.z, m0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int o = o0 + ty + 8 * i, m = m0 + tx;
+        float v = 0.f;
+        if (m < M && o < O) {
+            const long long e = ((long long)b * O + o) * M + m;
+            v = __ldg(out + e) > 0.f ? __ldg(gout + e) : 0.f;
+        }
+        t[ty + 8 * i][tx] = v;                      // [o][m]
+    }
+    __syncthreads();
+    const int o = o0 + tx;
+    float sb = 0.f, sg = 0.f;
+    if (o < O) {
+        const float mu = __ldg(mean + o), is = __ldg(invstd + o), gh = __ldg(gamma + o) * is;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int m = m0 + ty + 8 * i;
+            if (m < M) {
+                const long long q = (long long)b * M + m;
+                const float g = t[tx][ty + 8 * i];
+                const float yh = (__ldg(ysel + q * O + o) - mu) * is;
+                sb += g;
+                sg += g * yh;
+                gy[q * O + o] = g * gh;
+            }
+        }
+    }
+    rb[ty][tx] = sb;
+    rg[ty][tx] = sg;
+    __syncthreads();
+    if (ty == 0 && o < O) {
+        float a = 0.f, c = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a += rb[i][tx]; c += rg[i][tx]; }
+        atomicAdd(dbeta + o, (double)a);
+        atomicAdd(dgamma + o, (double)c);
+    }
+}
+
+// per support point: cnt[b,n] = #grouped positions that reference it, dpsum[b,n,:] = sum of their relative
+// coordinates; mom[0..2] = sum_p dp, mom[3..11] = sum_p dp dp^T  (f64)
+__global__ void __launch_bounds__(256)
+fused_sa_moments_kernel(int B, int N, int M, int NS, float inv_radius, const float *__restrict__ xyz,
+                        const float *__restrict__ qxyz, const int *__restrict__ idx, float *__restrict__ cnt,
+                        float *__restrict__ dpsum, double *__restrict__ mom) {
+    const long long P = (long long)B * M * NS;
+    const long long p = (long long)blockIdx.x * 256 + threadIdx.x;
+    float d[3] = {0.f, 0.f, 0.f};
+    if (p < P) {
+        const long long q = p / NS;
+        const long long b = q / M;
+        const long long row = b * N + __ldg(idx + p);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) d[j] = (__ldg(xyz + row * 3 + j) - __ldg(qxyz + q * 3 + j)) * inv_radius;
+        atomicAdd(cnt + row, 1.f);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) atomicAdd(dpsum + row * 3 + j, d[j]);
+    }
+    float v[12] = {d[0], d[1], d[2], d[0] * d[0], d[0] * d[1], d[0] * d[2], d[1] * d[0], d[1] * d[1], d[1] * d[2],
+                   d[2] * d[0], d[2] * d[1], d[2] * d[2]};
+    __shared__ float red[8][12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+        const float s = warp_sum(v[j]);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][j] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+        atomicAdd(mom + threadIdx.x, (double)s);
+    }
+}
+
+struct FusedBwdArgs {
+    const float *fT, *xyz, *qxyz;   // as in the forward
+    const int *idx;
+    const float *gy;                // (B*M, O)  ghat_o * G'[q,o]
+    const unsigned char *arg;       // (B*M, O)
+    const float *wT;                // (C, Op): W'[:, :C] transposed, Op = O rounded up to 32, zero padded
+    float *dfT;                     // (B, N, C) accumulator (holds the dense terms on entry)
+    float *E;                       // (O, Kp) sparse part of dW' (zeroed by the caller)
+    int B, N, M, C, O, Op, Kp, qchunk;
+    float inv_radius;
+};
+
+// dx[p, c] = sum_o dY[p,o] * W'[o,c]  as  D[c, p] = sum_o wT[c,o] * dY[p,o]  (M = 128 channels, N = 128 positions,
+// reduction over O in 128-byte chunks), dY built on the fly from (gy, arg); the epilogue thread that owns channel
+// c adds its row into the (B,N,C) accumulator: a warp's 32 lanes hit 128 contiguous bytes per position.
+template <int NS, bool X3>
+__global__ void __launch_bounds__(FS_THREADS, 3)
+fused_sa_bwd_dx_kernel(const FusedBwdArgs a) {
+    constexpr int QPT = FS_NT / NS;
+    constexpr int STAGES = 2;
+    extern __shared__ __align__(1024) unsigned char fs_smem_raw[];
+    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(fs_smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t t_bytes = FS_NT * FS_ROWB;                       // both operand tiles are 128 rows x 128 B
+    const uint32_t stage_bytes = (X3 ? 4u : 2u) * t_bytes;          // [dY hi | dY lo | wT hi | wT lo]
+    __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const long long Q = (long long)a.B * a.M;
+    const long long q0 = (long long)blockIdx.x * QPT;
+    const int c0 = blockIdx.y * 128;
+    const int nchunks = a.Op / 32;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(fs_smem(&bars[s]), FS_PROD);
+            mbar_init(fs_smem(&bars[STAGES + s]), 1);
+        }
+        mbar_init(fs_smem(&bars[2 * STAGES]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(fs_smem(&tmem_base_s)), "r"(128u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp < 4) {
+        const int slot = tid & 7, rsub = tid >> 3;
+        for (int kc = 0; kc < nchunks; ++kc) {
+            const int st = kc % STAGES;
+            if (kc >= STAGES) mbar_wait(fs_smem(&bars[STAGES + st]), (uint32_t)((kc / STAGES - 1) & 1));
+            unsigned char *ys = base + (size_t)st * stage_bytes;
+            unsigned char *yl = ys + t_bytes;
+            unsigned char *ws = ys + (X3 ? 2u : 1u) * t_bytes;
+            unsigned char *wl = ws + t_bytes;
+            const int o4 = kc * 32 + slot * 4;
+            // dY rows: position r = (query r / NS, sample r % NS)
+#pragma unroll
+            for (int i = 0; i < FS_NT / 16; ++i) {
+                const int r = i * 16 + rsub;
+                const long long qg = q0 + r / NS;
+                const uint32_t s = (uint32_t)(r % NS);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (qg < Q && o4 < a.O) {
+                    const uint32_t a4 = __ldg(reinterpret_cast<const uint32_t *>(a.arg + qg * a.O + o4));
+                    const float4 g = __ldg(reinterpret_cast<const float4 *>(a.gy + qg * a.O + o4));
+                    v.x = (a4 & 0xffu) == s ? g.x : 0.f;
+                    v.y = ((a4 >> 8) & 0xffu) == s ? g.y : 0.f;
+                    v.z = ((a4 >> 16) & 0xffu) == s ? g.z : 0.f;
+                    v.w = (a4 >> 24) == s ? g.w : 0.f;
+                }
+                fs_store<X3>(ys, yl, sw128_off(r, slot), v);
+            }
+            // wT rows: channel c0 + r
+#pragma unroll
+            for (int i = 0; i < FS_NT / 16; ++i) {
+                const int r = i * 16 + rsub;
+                const int c = c0 + r;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c < a.C) v = __ldg(reinterpret_cast<const float4 *>(a.wT + (long long)c * a.Op + o4));
+                fs_store<X3>(ws, wl, sw128_off(r, slot), v);
+            }
+            fence_async_smem();
+            mbar_arrive(fs_smem(&bars[st]));
+        }
+        // epilogue: scatter-add the rows of this tile
+        mbar_wait(fs_smem(&bars[2 * STAGES]), 0);
+        tc_fence_after();
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const int c = c0 + tid;
+#pragma unroll 1
+        for (int qi = 0; qi < QPT; ++qi) {
+            float v[NS];
+            __syncwarp();
+            tmem_ld_query<NS>(lane_addr + (uint32_t)(qi * NS), v);
+            const long long qg = q0 + qi;
+            if (qg >= Q) continue;                                   // warp-uniform
+            const long long b = qg / a.M;
+            const int n_mine = __ldg(a.idx + qg * NS + (tid & (NS - 1)));       // lane s holds idx[q][s]
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const int n = __shfl_sync(0xffffffffu, n_mine, s);
+                if (c < a.C && v[s] != 0.f) atomicAdd(a.dfT + (b * a.N + n) * a.C + c, v[s]);
+            }
+        }
+        tc_fence_before();
+    } else {
+        const uint32_t idesc = umma_idesc_tf32(128, FS_NT);
+        for (int kc = 0; kc < nchunks; ++kc) {
+            const int st = kc % STAGES;
+            mbar_wait(fs_smem(&bars[st]), (uint32_t)((kc / STAGES) & 1));
+            tc_fence_after();
+            if ((tid & 31) == 0) {
+                const uint32_t ys = fs_smem(base + (size_t)st * stage_bytes);
+                const uint32_t yl = ys + t_bytes;
+                const uint32_t ws = ys + (X3 ? 2u : 1u) * t_bytes;
+                const uint32_t wl = ws + t_bytes;
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint32_t acc = (kc > 0 || ks > 0) ? 1u : 0u;
+                    const uint64_t da = umma_desc_sw128(ws + ks * 32), db = umma_desc_sw128(ys + ks * 32);
+                    if (X3) {
+                        umma_tf32(tmem_base, umma_desc_sw128(wl + ks * 32), db, idesc, acc);
+                        umma_tf32(tmem_base, da, umma_desc_sw128(yl + ks * 32), idesc, 1u);
+                        umma_tf32(tmem_base, da, db, idesc, 1u);
+                    } else {
+                        umma_tf32(tmem_base, da, db, idesc, acc);
+                    }
+                }
+                umma_commit(fs_smem(&bars[STAGES + st]));
+                if (kc == nchunks - 1) umma_commit(fs_smem(&bars[2 * STAGES]));
+            }
+            __syncwarp();
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+    }
+}
+
+// E[o, k] += sum_{q in chunk} gy[q,o] * x[(q, arg[q,o]), k]  for one 32-float slice of K and 128 channels:
+// the rows of 128/NS queries are gathered into shared memory (double-buffered cp.async), every thread (one
+// channel) reads the one row its arg-max points to.  1/NS of the dense weight-gradient work, on the CUDA cores.
+constexpr int DW_LD = 36;            // floats per staged row: 144 B keeps float4 rows 16-byte aligned and spreads banks
+
+template <int NS>
+__global__ void __launch_bounds__(128)
+fused_sa_bwd_dw_kernel(const FusedBwdArgs a) {
+    constexpr int QPT = FS_NT / NS;
+    __shared__ __align__(16) float xs[2][FS_NT * DW_LD];
+    const int tid = threadIdx.x, slot = tid & 7, rsub = tid >> 3;
+    const int k0 = blockIdx.x * 32;
+    const int o = blockIdx.z * 128 + tid;
+    const long long Q = (long long)a.B * a.M;
+    const long long nit_all = (Q + QPT - 1) / QPT;
+    const long long it0 = (long long)blockIdx.y * a.qchunk, it1 = min(nit_all, it0 + a.qchunk);
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+
+    auto load = [&](long long it, int buf) {
+        const long long q0 = it * QPT;
+        const int kk = k0 + slot * 4;
+#pragma unroll
+        for (int i = 0; i < FS_NT / 16; ++i) {
+            const int r = i * 16 + rsub;
+            const long long qg = q0 + r / NS;
+            float *dst = &xs[buf][r * DW_LD + slot * 4];
+            bool feat = false;
+            long long row = 0;
+            if (qg < Q) {
+                row = (qg / a.M) * a.N + __ldg(a.idx + qg * NS + (r % NS));
+                feat = kk + 4 <= a.C;
+            }
+            if (qg < Q && kk == a.C) {
+                const float *pp = a.xyz + row * 3, *qq = a.qxyz + qg * 3;
+                *reinterpret_cast<float4 *>(dst) = make_float4((__ldg(pp) - __ldg(qq)) * a.inv_radius,
+                                                               (__ldg(pp + 1) - __ldg(qq + 1)) * a.inv_radius,
+                                                               (__ldg(pp + 2) - __ldg(qq + 2)) * a.inv_radius, 0.f);
+            } else {
+                cp_async16(fs_smem(dst), feat ? a.fT + row * a.C + kk : a.fT, feat);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (it0 < it1) load(it0, 0);
+    for (long long it = it0; it < it1; ++it) {
+        const int buf = (int)((it - it0) & 1);
+        if (it + 1 < it1) load(it + 1, buf ^ 1);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        if (o < a.O) {
+#pragma unroll
+            for (int qi = 0; qi < QPT; ++qi) {
+                const long long qg = it * QPT + qi;
+                if (qg < Q) {
+                    const float g = __ldg(a.gy + qg * a.O + o);
+                    if (g != 0.f) {
+                        const int s = __ldg(a.arg + qg * a.O + o);
+                        const float4 *row = reinterpret_cast<const float4 *>(&xs[buf][(qi * NS + s) * DW_LD]);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 x = row[j];
+                            acc[4 * j] = fmaf(g, x.x, acc[4 * j]);
+                            acc[4 * j + 1] = fmaf(g, x.y, acc[4 * j + 1]);
+                            acc[4 * j + 2] = fmaf(g, x.z, acc[4 * j + 2]);
+                            acc[4 * j + 3] = fmaf(g, x.w, acc[4 * j + 3]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (o < a.O) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (k0 + j < a.Kp && acc[j] != 0.f) atomicAdd(a.E + (long long)o * a.Kp + k0 + j, acc[j]);
+    }
+}
+
+}  // namespace amc3d
+
+extern "C" int amc3d_fused_sa_backward_prep(int b, int m, int o, const float *grad_out, const float *out,
+                                            const float *ysel, const float *mean, const float *invstd,
+                                            const float *gamma, float *gy, double *dbeta_dgamma, void *stream) {
+    AMC3D_REQUIRE(b >= 0 && m >= 0 && o >= 1, AMC3D_EINVAL, "fused_sa_backward_prep: bad sizes");
+    AMC3D_REQUIRE(b <= 65535, AMC3D_ELIMIT, "fused_sa_backward_prep: batch %d > 65535", b);
+    cudaStream_t st = as_stream(stream);
+    cudaMemsetAsync(dbeta_dgamma, 0, sizeof(double) * 2 * (size_t)o, st);
+    if (b == 0 || m == 0) return check_launch("fused_sa_backward_prep");
+    dim3 grid(div_up(m, 32), div_up(o, 32), b);
+    fused_sa_bwd_prep_kernel<<<grid, 256, 0, st>>>(b, m, o, grad_out, out, ysel, mean, invstd, gamma, gy,
+                                                   dbeta_dgamma, dbeta_dgamma + o);
+    return check_launch("fused_sa_backward_prep");
+}
+
+extern "C" int amc3d_fused_sa_moments(int b, int n, int m, int nsample, float radius, int normalize_dp,
+                                      const float *xyz, const float *new_xyz, const int *idx, float *cnt,
+                                      float *dpsum, double *mom, void *stream) {
+    AMC3D_REQUIRE(b >= 0 && n >= 1 && m >= 0 && nsample >= 1, AMC3D_EINVAL, "fused_sa_moments: bad sizes");
+    cudaStream_t st = as_stream(stream);
+    cudaMemsetAsync(cnt, 0, sizeof(float) * (size_t)b * n, st);
+    cudaMemsetAsync(dpsum, 0, sizeof(float) * 3 * (size_t)b * n, st);
+    cudaMemsetAsync(mom, 0, sizeof(double) * 12, st);
+    const long long P = (long long)b * m * nsample;
+    if (P > 0)
+        fused_sa_moments_kernel<<<(unsigned)div_up_ll(P, 256), 256, 0, st>>>(b, n, m, nsample, normalize_dp ? 1.0f / radius : 1.0f,
+                                                                              xyz, new_xyz, idx, cnt, dpsum, mom);
+    return check_launch("fused_sa_moments");
+}
+
+template <int NS, bool X3>
+static int launch_fused_dx(const FusedBwdArgs &a, cudaStream_t st) {
+    const size_t smem = 2 * (size_t)(X3 ? 4 : 2) * FS_NT * FS_ROWB + 1024;
+    cudaError_t e = cudaFuncSetAttribute(fused_sa_bwd_dx_kernel<NS, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(fused_sa_bwd_dx_kernel<NS, X3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
+    const long long Q = (long long)a.B * a.M;
+    dim3 grid((unsigned)div_up_ll(Q, FS_NT / NS), (unsigned)div_up(a.C, 128));
+    fused_sa_bwd_dx_kernel<NS, X3><<<grid, FS_THREADS, smem, st>>>(a);
+    return 0;
+}
+
+extern "C" int amc3d_fused_sa_backward_sparse(int b, int n, int m, int c, int o, int o_padded, int nsample, float radius,
+                                              int normalize_dp, int precision, const float *featT, const float *xyz,
+                                              const float *new_xyz, const int *idx, const float *gy,
+                                              const unsigned char *arg, const float *w_t, float *dfeatT,
+                                              float *dw_packed, void *stream) {
+    AMC3D_REQUIRE(b >= 0 && n >= 1 && m >= 0 && c >= 8 && o >= 1, AMC3D_EINVAL, "fused_sa_backward_sparse: bad sizes");
+    AMC3D_REQUIRE(c % 8 == 0 && o % 4 == 0 && o_padded % 32 == 0 && o_padded >= o, AMC3D_ELIMIT,
+                  "fused_sa_backward_sparse: C=%d must be a multiple of 8, O=%d of 4, O_padded=%d of 32", c, o, o_padded);
+    AMC3D_REQUIRE(nsample == 16 || nsample == 32, AMC3D_ELIMIT, "fused_sa_backward_sparse: nsample=%d", nsample);
+    AMC3D_REQUIRE(precision == 1 || precision == 3, AMC3D_EINVAL, "fused_sa_backward_sparse: precision=%d", precision);
+    if (b == 0 || m == 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    FusedBwdArgs a;
+    a.fT = featT; a.xyz = xyz; a.qxyz = new_xyz; a.idx = idx; a.gy = gy; a.arg = arg; a.wT = w_t; a.dfT = dfeatT;
+    a.E = dw_packed; a.B = b; a.N = n; a.M = m; a.C = c; a.O = o; a.Op = o_padded; a.Kp = c + 8;
+    a.inv_radius = normalize_dp ? 1.0f / radius : 1.0f;
+    // sparse weight gradient
+    const int nk = div_up(c + 3, 32), nz = div_up(o, 128);
+    const long long nit = div_up_ll((long long)b * m, FS_NT / nsample);
+    long long chunks = max(1ll, min(nit / 4, (long long)(8 * kNumSMs) / ((long long)nk * nz)));
+    chunks = min(chunks, 65535ll);
+    a.qchunk = (int)div_up_ll(nit, chunks);
+    dim3 wgrid(nk, (unsigned)div_up_ll(nit, a.qchunk), nz);
+    if (nsample == 32) fused_sa_bwd_dw_kernel<32><<<wgrid, 128, 0, st>>>(a);
+    else fused_sa_bwd_dw_kernel<16><<<wgrid, 128, 0, st>>>(a);
+    // sparse input gradient, scatter-added into dfeatT
+    int rc;
+    if (nsample == 32) rc = precision == 3 ? launch_fused_dx<32, true>(a, st) : launch_fused_dx<32, false>(a, st);
+    else rc = precision == 3 ? launch_fused_dx<16, true>(a, st) : launch_fused_dx<16, false>(a, st);
+    if (rc != 0) {
+        set_error("fused_sa_backward_sparse: %s", cudaGetErrorString((cudaError_t)rc));
+        return rc;
+    }
+    return check_launch("fused_sa_backward_sparse");
+}

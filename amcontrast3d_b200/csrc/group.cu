@@ -720,6 +720,15 @@ static int group_common(bool fwd, int b, int c, int n, long long P, const float 
     return check_launch(what);
 }
 
+// (B, rows, cols) -> (B, cols, rows): the channel-contiguous copy the fused operator gathers from
+extern "C" int amc3d_transpose_batched(int b, int rows, int cols, const float *src, float *dst, void *stream) {
+    AMC3D_REQUIRE(b >= 0 && rows >= 0 && cols >= 0, AMC3D_EINVAL, "transpose_batched: negative size");
+    AMC3D_REQUIRE(b <= 65535, AMC3D_ELIMIT, "transpose_batched: batch %d > 65535", b);
+    if (b == 0 || rows == 0 || cols == 0) return 0;
+    launch_transpose<false>(b, rows, cols, src, dst, as_stream(stream));
+    return check_launch("transpose_batched");
+}
+
 extern "C" int amc3d_group_points_ws(int b, int c, int n, int npoints, int nsample, const float *points,
                                      const int *idx, float *out, float *workspace, void *stream) {
     AMC3D_REQUIRE(b >= 0 && c >= 0 && n >= 0 && npoints >= 0 && nsample >= 0, AMC3D_EINVAL,

@@ -153,6 +153,56 @@ int amc3d_three_interpolate_grad_ws_set(int b, int c, int n, int m, const float 
                                         const int *idx, const float *weight, float *grad_points,
                                         float *workspace, void *stream);
 
+/* (B, rows, cols) -> (B, cols, rows), e.g. features (B,C,N) -> the channel-contiguous (B,N,C) copy the fused
+ * operator below gathers from (torch's x.transpose(1, 2).contiguous(), as one tiled kernel). */
+int amc3d_transpose_batched(int b, int rows, int cols, const float *src, float *dst, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused  grouping -> 1x1 conv -> BatchNorm (training statistics) -> ReLU -> max over nsample
+ * (SURVEY.md §8f rank 1).  Replaces, for one conv layer, the module composition
+ *   QueryAndGroup + cat(dp, fj) + Conv2d(3+C, O, 1, bias=False) + BatchNorm2d(O) + ReLU + max(dim=-1)
+ * ref: models/backbone/pointnext_AA.py:57-63 LocalAggregation.forward, :139-170 SetAbstraction.forward,
+ *      models/layers/group.py:235-255 QueryAndGroup.forward, models/layers/conv.py:24-61 create_convblock2d.
+ * The grouped tensor (B, 3+C, M, nsample) is never materialised: tcgen05 MMAs (TF32 operands, FP32
+ * accumulators in TMEM) read neighbour rows gathered straight into the swizzled operand tile.
+ *   featT (B,N,C)   channel-contiguous features (amc3d_transpose_batched of the module's (B,C,N) input)
+ *   xyz (B,N,3) support, new_xyz (B,M,3) queries, idx (B,M,nsample) i32 from amc3d_ball_query
+ *   w_packed (O, C+8) = [W[:, 3:3+C] | W[:, 0:3] | 0 0 0 0 0]  (conv weight with the 3 dp columns moved
+ *                       behind the features, rows padded to a multiple of 8 floats)
+ *   precision 1 = TF32 operands (cuDNN's default for the reference's Conv2d), 3 = 3xTF32 (FP32-faithful)
+ * Outputs: out (B,O,M); mean/var (O) the batch statistics (var biased, as normalisation uses it);
+ * invstd (O); and, kept for the backward: ysel (B*M,O) the pre-normalisation extreme of each (query,
+ * channel), arg (B*M,O) u8 its sample index; sums (128*O) f64 scratch (64 replicas of sum y, sum y^2).
+ * Limits: C % 8 == 0, nsample in {16, 32}. */
+int amc3d_fused_sa_forward(int b, int n, int m, int c, int o, int nsample, float radius, int normalize_dp,
+                           int precision, float eps, const float *featT, const float *xyz,
+                           const float *new_xyz, const int *idx, const float *w_packed,
+                           const float *gamma, const float *beta, float *ysel, unsigned char *arg,
+                           double *sums, float *mean, float *var, float *invstd, float *out, void *stream);
+
+/* Backward of amc3d_fused_sa_forward, in three device steps around a few small library GEMMs on the host
+ * side (amcontrast3d_b200/layers/_fused_backward.py has the algebra; csrc/fused_sa.cu the derivation):
+ *  _backward_prep    gy (B*M,O) = grad_out * [out > 0] * gamma * invstd, transposed to query-major;
+ *                    dbeta_dgamma (2*O) f64 = [sum D, sum D * yhat]
+ *  _moments          per support point cnt (B,N) f32 and dpsum (B,N,3) f32 (how often / with which relative
+ *                    coordinates it is grouped) and mom (12) f64 = [sum dp (3) | sum dp dp^T (9)]: with these
+ *                    the dense BatchNorm terms of the gradient reduce to (B*N) x C x C GEMMs
+ *  _backward_sparse  the arg-max terms: dw_packed (O, C+8) += sum_q gy[q,o] * x[arg-max row]  (zeroed by the
+ *                    caller) and dfeatT (B,N,C) += scatter-add of  sum_o dY[p,o] W'[o,:]  (tcgen05, dY built
+ *                    on the fly; holds the dense terms on entry).  w_t (C, o_padded) = W'[:, :C]^T, zero padded
+ *                    to o_padded = O rounded up to 32. */
+int amc3d_fused_sa_backward_prep(int b, int m, int o, const float *grad_out, const float *out,
+                                 const float *ysel, const float *mean, const float *invstd,
+                                 const float *gamma, float *gy, double *dbeta_dgamma, void *stream);
+int amc3d_fused_sa_moments(int b, int n, int m, int nsample, float radius, int normalize_dp,
+                           const float *xyz, const float *new_xyz, const int *idx, float *cnt,
+                           float *dpsum, double *mom, void *stream);
+int amc3d_fused_sa_backward_sparse(int b, int n, int m, int c, int o, int o_padded, int nsample, float radius,
+                                   int normalize_dp, int precision, const float *featT, const float *xyz,
+                                   const float *new_xyz, const int *idx, const float *gy,
+                                   const unsigned char *arg, const float *w_t, float *dfeatT,
+                                   float *dw_packed, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * pointops family: packed (n,3) xyz / (n,c) features with cumulative i32 `offset` ends
  * ------------------------------------------------------------------------------------- */
