@@ -58,9 +58,8 @@ SIGNATURES = {
     "amc3d_transpose_batched": [_I, _I, _I, _P, _P, _P],
     "amc3d_fused_sa_forward": [_I, _I, _I, _I, _I, _I, _F, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                _P, _P, _P],
-    "amc3d_fused_sa_backward_prep": [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "amc3d_fused_sa_backward_scatter": [_I, _I, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "amc3d_fused_sa_moments": [_I, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P],
-    "amc3d_fused_sa_backward_sparse": [_I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "amc3d_three_nn": [_I, _I, _I, _P, _P, _P, _P, _P],
     "amc3d_three_interpolate": [_I, _I, _I, _I, _P, _P, _P, _P, _P],
     "amc3d_three_interpolate_grad": [_I, _I, _I, _I, _P, _P, _P, _P, _P],
@@ -160,8 +159,6 @@ def _kernels_in(name: str, args) -> int:
         return 2 if args[-2] else 1            # scatter + transpose-accumulate (plus a memset)
     if name == "amc3d_fused_sa_forward":
         return 3                               # GEMM + statistics + normalise
-    if name == "amc3d_fused_sa_backward_sparse":
-        return 2                               # sparse dW + tcgen05 dX
     if name in ("amc3d_refine_backward", "amc3d_ambiguity", "amc3d_ambiguity_backend"):
         return 2                               # (boundary count + ambiguity)
     return 1

@@ -454,8 +454,11 @@ extern "C" int amc3d_fused_sa_forward(int b, int n, int m, int c, int o, int nsa
     static const int env_oc = getenv("AMC3D_FUSED_OC") ? atoi(getenv("AMC3D_FUSED_OC")) : 0;
     static const int env_st = getenv("AMC3D_FUSED_STAGES") ? atoi(getenv("AMC3D_FUSED_STAGES")) : 0;
     const int ocmax = precision == 3 ? 256 : 512;                   // shared-memory budget of a stage
-    a.oc = opad <= 128 ? 128 : (opad <= 256 || ocmax == 256 ? 256 : 512);
-    if (env_oc == 128 || env_oc == 256 || (env_oc == 512 && ocmax == 512)) a.oc = min(env_oc, a.oc);
+    // 128 channels per CTA measured best (more CTAs per SM beat the reuse of the gathered tile: case table in
+    // profiles/r02_fused.md); AMC3D_FUSED_OC = 256 / 512 widens it
+    a.oc = 128;
+    if (env_oc == 256 || (env_oc == 512 && ocmax == 512)) a.oc = min(env_oc, opad <= 128 ? 128 : (opad <= 256 ? 256 : 512));
+    (void)ocmax;
     a.stages = 2;
     if (env_st >= 2 && env_st <= FS_MAX_STAGES) a.stages = env_st;
     while (a.stages > 2 && (size_t)a.stages * (precision == 3 ? 2 : 1) * (FS_NT * FS_ROWB + (size_t)a.oc * FS_ROWB) + 2048 > 227 * 1024) --a.stages;
@@ -482,23 +485,30 @@ namespace amc3d {
 //   dbeta   = sum_p D            dgamma = sum_p D * yhat
 //   dL/dy[p,o] = ghat_o * D[p,o] - c0_o - c1_o * y[p,o]     ghat = gamma*invstd, c1 = ghat*invstd*dgamma/P,
 //                                                           c0 = ghat*dbeta/P - c1*mean
-// The two terms without D are DENSE over all P positions but linear in x, so they reduce to the first and second
-// moments of the grouped input (sum_p x, sum_p x x^T), which in turn reduce to per-support-point counts because
-// x[p] = [f[idx[p]] | dp[p]]:  sum_p f[idx[p]] f[idx[p]]^T = sum_n cnt[n] f[n] f[n]^T — plain (B*N) x C x C GEMMs, 1/ns
-// of the convolution's work, done by the host side with library GEMMs.  The D terms are SPARSE (1/ns dense):
-//   dW[o,:]  += ghat_o * sum_q G'[q,o] * x[p*(q,o), :]                    fused_sa_bwd_dw_kernel  (CUDA cores)
-//   dx[p,:]  += sum_o ghat_o * D[p,o] * W[o,:]   -> scatter-add to df      fused_sa_bwd_dx_kernel  (tcgen05)
-// Nothing of size P x (3+C) or P x O is ever stored.
+// The two terms without D are dense over all P positions but linear in x, so they reduce to the first and second
+// moments of the grouped input, which reduce to per-support-point counts because x[p] = [f[idx[p]] | dp[p]]:
+// sum_p f[idx[p]] f[idx[p]]^T = sum_n cnt[n] f[n] f[n]^T  (fused_sa_moments_kernel + (B*N) x C x C GEMMs).
+// The D term is sparse, and its target only depends on WHICH support point the arg-max position refers to:
+//   A[n, o] = sum_{q : idx[q, arg(q,o)] = n} ghat_o * G'[q,o]                      (fused_sa_bwd_scatter_kernel)
+//   dW_f = A^T f        df = A W_f        dW_dp[o,:] = sum_q ghat_o G'[q,o] dp[(q, arg(q,o)), :]
+// i.e. one scatter of Q*O scalars followed by two (B*N) x O x C GEMMs — 1/nsample of the convolution's work —
+// instead of the two convolution-sized products a dense backward would need.  The GEMMs are plain library calls
+// on the host side (layers/_fused_backward.py).  Nothing of size P x (3+C) or P x O is ever stored.
 // =================================================================================================================
 
-// gy[q,o] = G[b,o,m] * [out[b,o,m] > 0] * gamma[o] * invstd[o]   ((B,O,M) -> (B*M,O));  dbeta, dgamma (f64, atomics)
+// For a 32 (queries) x 32 (channels) tile: G' = G * [out > 0]; dbeta, dgamma (f64 atomics); the scatter into
+// A (B*N, O) (lanes = consecutive channels: 128 contiguous bytes per warp and query); dW of the three
+// relative-coordinate columns, wdp (O, 3) f64.
 __global__ void __launch_bounds__(256)
-fused_sa_bwd_prep_kernel(int B, int M, int O, const float *__restrict__ gout, const float *__restrict__ out,
-                         const float *__restrict__ ysel, const float *__restrict__ mean,
-                         const float *__restrict__ invstd, const float *__restrict__ gamma, float *__restrict__ gy,
-                         double *__restrict__ dbeta, double *__restrict__ dgamma) {
+fused_sa_bwd_scatter_kernel(int B, int N, int M, int O, int NS, float inv_radius, const float *__restrict__ gout,
+                            const float *__restrict__ out, const float *__restrict__ ysel,
+                            const unsigned char *__restrict__ arg, const int *__restrict__ idx,
+                            const float *__restrict__ xyz, const float *__restrict__ qxyz,
+                            const float *__restrict__ mean, const float *__restrict__ invstd,
+                            const float *__restrict__ gamma, float *__restrict__ A, double *__restrict__ dbeta,
+                            double *__restrict__ dgamma, double *__restrict__ wdp) {
     __shared__ float t[32][33];
-    __shared__ float rb[8][32], rg[8][32];
+    __shared__ float red[5][8][32];
     const int b = blockIdx.z, m0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll
@@ -513,7 +523,7 @@ fused_sa_bwd_prep_kernel(int B, int M, int O, const float *__restrict__ gout, co
     }
     __syncthreads();
     const int o = o0 + tx;
-    float sb = 0.f, sg = 0.f;
+    float sb = 0.f, sg = 0.f, sd[3] = {0.f, 0.f, 0.f};
     if (o < O) {
         const float mu = __ldg(mean + o), is = __ldg(invstd + o), gh = __ldg(gamma + o) * is;
 #pragma unroll
@@ -522,22 +532,32 @@ fused_sa_bwd_prep_kernel(int B, int M, int O, const float *__restrict__ gout, co
             if (m < M) {
                 const long long q = (long long)b * M + m;
                 const float g = t[tx][ty + 8 * i];
-                const float yh = (__ldg(ysel + q * O + o) - mu) * is;
-                sb += g;
-                sg += g * yh;
-                gy[q * O + o] = g * gh;
+                if (g != 0.f) {
+                    const float yh = (__ldg(ysel + q * O + o) - mu) * is;
+                    sb += g;
+                    sg += g * yh;
+                    const int s = __ldg(arg + q * O + o);
+                    const long long row = (long long)b * N + __ldg(idx + q * NS + s);
+                    const float gg = g * gh;
+                    atomicAdd(A + row * O + o, gg);
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+                        sd[j] += gg * ((__ldg(xyz + row * 3 + j) - __ldg(qxyz + q * 3 + j)) * inv_radius);
+                }
             }
         }
     }
-    rb[ty][tx] = sb;
-    rg[ty][tx] = sg;
+    red[0][ty][tx] = sb; red[1][ty][tx] = sg; red[2][ty][tx] = sd[0]; red[3][ty][tx] = sd[1]; red[4][ty][tx] = sd[2];
     __syncthreads();
-    if (ty == 0 && o < O) {
-        float a = 0.f, c = 0.f;
+    if (ty < 5 && o < O) {
+        float a = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { a += rb[i][tx]; c += rg[i][tx]; }
-        atomicAdd(dbeta + o, (double)a);
-        atomicAdd(dgamma + o, (double)c);
+        for (int i = 0; i < 8; ++i) a += red[ty][i][tx];
+        if (a != 0.f) {
+            if (ty == 0) atomicAdd(dbeta + o, (double)a);
+            else if (ty == 1) atomicAdd(dgamma + o, (double)a);
+            else atomicAdd(wdp + o * 3 + (ty - 2), (double)a);
+        }
     }
 }
 
@@ -577,247 +597,25 @@ fused_sa_moments_kernel(int B, int N, int M, int NS, float inv_radius, const flo
     }
 }
 
-struct FusedBwdArgs {
-    const float *fT, *xyz, *qxyz;   // as in the forward
-    const int *idx;
-    const float *gy;                // (B*M, O)  ghat_o * G'[q,o]
-    const unsigned char *arg;       // (B*M, O)
-    const float *wT;                // (C, Op): W'[:, :C] transposed, Op = O rounded up to 32, zero padded
-    float *dfT;                     // (B, N, C) accumulator (holds the dense terms on entry)
-    float *E;                       // (O, Kp) sparse part of dW' (zeroed by the caller)
-    int B, N, M, C, O, Op, Kp, qchunk;
-    float inv_radius;
-};
-
-// dx[p, c] = sum_o dY[p,o] * W'[o,c]  as  D[c, p] = sum_o wT[c,o] * dY[p,o]  (M = 128 channels, N = 128 positions,
-// reduction over O in 128-byte chunks), dY built on the fly from (gy, arg); the epilogue thread that owns channel
-// c adds its row into the (B,N,C) accumulator: a warp's 32 lanes hit 128 contiguous bytes per position.
-template <int NS, bool X3>
-__global__ void __launch_bounds__(FS_THREADS, 3)
-fused_sa_bwd_dx_kernel(const FusedBwdArgs a) {
-    constexpr int QPT = FS_NT / NS;
-    constexpr int STAGES = 2;
-    extern __shared__ __align__(1024) unsigned char fs_smem_raw[];
-    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(fs_smem_raw) + 1023) & ~(uintptr_t)1023);
-    const uint32_t t_bytes = FS_NT * FS_ROWB;                       // both operand tiles are 128 rows x 128 B
-    const uint32_t stage_bytes = (X3 ? 4u : 2u) * t_bytes;          // [dY hi | dY lo | wT hi | wT lo]
-    __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
-    __shared__ uint32_t tmem_base_s;
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const long long Q = (long long)a.B * a.M;
-    const long long q0 = (long long)blockIdx.x * QPT;
-    const int c0 = blockIdx.y * 128;
-    const int nchunks = a.Op / 32;
-
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(fs_smem(&bars[s]), FS_PROD);
-            mbar_init(fs_smem(&bars[STAGES + s]), 1);
-        }
-        mbar_init(fs_smem(&bars[2 * STAGES]), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 4) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(fs_smem(&tmem_base_s)), "r"(128u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = tmem_base_s;
-
-    if (warp < 4) {
-        const int slot = tid & 7, rsub = tid >> 3;
-        for (int kc = 0; kc < nchunks; ++kc) {
-            const int st = kc % STAGES;
-            if (kc >= STAGES) mbar_wait(fs_smem(&bars[STAGES + st]), (uint32_t)((kc / STAGES - 1) & 1));
-            unsigned char *ys = base + (size_t)st * stage_bytes;
-            unsigned char *yl = ys + t_bytes;
-            unsigned char *ws = ys + (X3 ? 2u : 1u) * t_bytes;
-            unsigned char *wl = ws + t_bytes;
-            const int o4 = kc * 32 + slot * 4;
-            // dY rows: position r = (query r / NS, sample r % NS)
-#pragma unroll
-            for (int i = 0; i < FS_NT / 16; ++i) {
-                const int r = i * 16 + rsub;
-                const long long qg = q0 + r / NS;
-                const uint32_t s = (uint32_t)(r % NS);
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (qg < Q && o4 < a.O) {
-                    const uint32_t a4 = __ldg(reinterpret_cast<const uint32_t *>(a.arg + qg * a.O + o4));
-                    const float4 g = __ldg(reinterpret_cast<const float4 *>(a.gy + qg * a.O + o4));
-                    v.x = (a4 & 0xffu) == s ? g.x : 0.f;
-                    v.y = ((a4 >> 8) & 0xffu) == s ? g.y : 0.f;
-                    v.z = ((a4 >> 16) & 0xffu) == s ? g.z : 0.f;
-                    v.w = (a4 >> 24) == s ? g.w : 0.f;
-                }
-                fs_store<X3>(ys, yl, sw128_off(r, slot), v);
-            }
-            // wT rows: channel c0 + r
-#pragma unroll
-            for (int i = 0; i < FS_NT / 16; ++i) {
-                const int r = i * 16 + rsub;
-                const int c = c0 + r;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (c < a.C) v = __ldg(reinterpret_cast<const float4 *>(a.wT + (long long)c * a.Op + o4));
-                fs_store<X3>(ws, wl, sw128_off(r, slot), v);
-            }
-            fence_async_smem();
-            mbar_arrive(fs_smem(&bars[st]));
-        }
-        // epilogue: scatter-add the rows of this tile
-        mbar_wait(fs_smem(&bars[2 * STAGES]), 0);
-        tc_fence_after();
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-        const int c = c0 + tid;
-#pragma unroll 1
-        for (int qi = 0; qi < QPT; ++qi) {
-            float v[NS];
-            __syncwarp();
-            tmem_ld_query<NS>(lane_addr + (uint32_t)(qi * NS), v);
-            const long long qg = q0 + qi;
-            if (qg >= Q) continue;                                   // warp-uniform
-            const long long b = qg / a.M;
-            const int n_mine = __ldg(a.idx + qg * NS + (tid & (NS - 1)));       // lane s holds idx[q][s]
-#pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                const int n = __shfl_sync(0xffffffffu, n_mine, s);
-                if (c < a.C && v[s] != 0.f) atomicAdd(a.dfT + (b * a.N + n) * a.C + c, v[s]);
-            }
-        }
-        tc_fence_before();
-    } else {
-        const uint32_t idesc = umma_idesc_tf32(128, FS_NT);
-        for (int kc = 0; kc < nchunks; ++kc) {
-            const int st = kc % STAGES;
-            mbar_wait(fs_smem(&bars[st]), (uint32_t)((kc / STAGES) & 1));
-            tc_fence_after();
-            if ((tid & 31) == 0) {
-                const uint32_t ys = fs_smem(base + (size_t)st * stage_bytes);
-                const uint32_t yl = ys + t_bytes;
-                const uint32_t ws = ys + (X3 ? 2u : 1u) * t_bytes;
-                const uint32_t wl = ws + t_bytes;
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint32_t acc = (kc > 0 || ks > 0) ? 1u : 0u;
-                    const uint64_t da = umma_desc_sw128(ws + ks * 32), db = umma_desc_sw128(ys + ks * 32);
-                    if (X3) {
-                        umma_tf32(tmem_base, umma_desc_sw128(wl + ks * 32), db, idesc, acc);
-                        umma_tf32(tmem_base, da, umma_desc_sw128(yl + ks * 32), idesc, 1u);
-                        umma_tf32(tmem_base, da, db, idesc, 1u);
-                    } else {
-                        umma_tf32(tmem_base, da, db, idesc, acc);
-                    }
-                }
-                umma_commit(fs_smem(&bars[STAGES + st]));
-                if (kc == nchunks - 1) umma_commit(fs_smem(&bars[2 * STAGES]));
-            }
-            __syncwarp();
-        }
-        tc_fence_before();
-    }
-    __syncthreads();
-    if (warp == 4) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
-    }
-}
-
-// E[o, k] += sum_{q in chunk} gy[q,o] * x[(q, arg[q,o]), k]  for one 32-float slice of K and 128 channels:
-// the rows of 128/NS queries are gathered into shared memory (double-buffered cp.async), every thread (one
-// channel) reads the one row its arg-max points to.  1/NS of the dense weight-gradient work, on the CUDA cores.
-constexpr int DW_LD = 36;            // floats per staged row: 144 B keeps float4 rows 16-byte aligned and spreads banks
-
-template <int NS>
-__global__ void __launch_bounds__(128)
-fused_sa_bwd_dw_kernel(const FusedBwdArgs a) {
-    constexpr int QPT = FS_NT / NS;
-    __shared__ __align__(16) float xs[2][FS_NT * DW_LD];
-    const int tid = threadIdx.x, slot = tid & 7, rsub = tid >> 3;
-    const int k0 = blockIdx.x * 32;
-    const int o = blockIdx.z * 128 + tid;
-    const long long Q = (long long)a.B * a.M;
-    const long long nit_all = (Q + QPT - 1) / QPT;
-    const long long it0 = (long long)blockIdx.y * a.qchunk, it1 = min(nit_all, it0 + a.qchunk);
-    float acc[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-
-    auto load = [&](long long it, int buf) {
-        const long long q0 = it * QPT;
-        const int kk = k0 + slot * 4;
-#pragma unroll
-        for (int i = 0; i < FS_NT / 16; ++i) {
-            const int r = i * 16 + rsub;
-            const long long qg = q0 + r / NS;
-            float *dst = &xs[buf][r * DW_LD + slot * 4];
-            bool feat = false;
-            long long row = 0;
-            if (qg < Q) {
-                row = (qg / a.M) * a.N + __ldg(a.idx + qg * NS + (r % NS));
-                feat = kk + 4 <= a.C;
-            }
-            if (qg < Q && kk == a.C) {
-                const float *pp = a.xyz + row * 3, *qq = a.qxyz + qg * 3;
-                *reinterpret_cast<float4 *>(dst) = make_float4((__ldg(pp) - __ldg(qq)) * a.inv_radius,
-                                                               (__ldg(pp + 1) - __ldg(qq + 1)) * a.inv_radius,
-                                                               (__ldg(pp + 2) - __ldg(qq + 2)) * a.inv_radius, 0.f);
-            } else {
-                cp_async16(fs_smem(dst), feat ? a.fT + row * a.C + kk : a.fT, feat);
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    if (it0 < it1) load(it0, 0);
-    for (long long it = it0; it < it1; ++it) {
-        const int buf = (int)((it - it0) & 1);
-        if (it + 1 < it1) load(it + 1, buf ^ 1);
-        else asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        __syncthreads();
-        if (o < a.O) {
-#pragma unroll
-            for (int qi = 0; qi < QPT; ++qi) {
-                const long long qg = it * QPT + qi;
-                if (qg < Q) {
-                    const float g = __ldg(a.gy + qg * a.O + o);
-                    if (g != 0.f) {
-                        const int s = __ldg(a.arg + qg * a.O + o);
-                        const float4 *row = reinterpret_cast<const float4 *>(&xs[buf][(qi * NS + s) * DW_LD]);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 x = row[j];
-                            acc[4 * j] = fmaf(g, x.x, acc[4 * j]);
-                            acc[4 * j + 1] = fmaf(g, x.y, acc[4 * j + 1]);
-                            acc[4 * j + 2] = fmaf(g, x.z, acc[4 * j + 2]);
-                            acc[4 * j + 3] = fmaf(g, x.w, acc[4 * j + 3]);
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-    }
-    if (o < a.O) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (k0 + j < a.Kp && acc[j] != 0.f) atomicAdd(a.E + (long long)o * a.Kp + k0 + j, acc[j]);
-    }
-}
-
 }  // namespace amc3d
 
-extern "C" int amc3d_fused_sa_backward_prep(int b, int m, int o, const float *grad_out, const float *out,
-                                            const float *ysel, const float *mean, const float *invstd,
-                                            const float *gamma, float *gy, double *dbeta_dgamma, void *stream) {
-    AMC3D_REQUIRE(b >= 0 && m >= 0 && o >= 1, AMC3D_EINVAL, "fused_sa_backward_prep: bad sizes");
-    AMC3D_REQUIRE(b <= 65535, AMC3D_ELIMIT, "fused_sa_backward_prep: batch %d > 65535", b);
+extern "C" int amc3d_fused_sa_backward_scatter(int b, int n, int m, int o, int nsample, float radius, int normalize_dp,
+                                               const float *grad_out, const float *out, const float *ysel,
+                                               const unsigned char *arg, const int *idx, const float *xyz,
+                                               const float *new_xyz, const float *mean, const float *invstd,
+                                               const float *gamma, float *a_scatter, double *dbeta_dgamma_wdp,
+                                               void *stream) {
+    AMC3D_REQUIRE(b >= 0 && n >= 1 && m >= 0 && o >= 1 && nsample >= 1, AMC3D_EINVAL, "fused_sa_backward_scatter: bad sizes");
+    AMC3D_REQUIRE(b <= 65535, AMC3D_ELIMIT, "fused_sa_backward_scatter: batch %d > 65535", b);
     cudaStream_t st = as_stream(stream);
-    cudaMemsetAsync(dbeta_dgamma, 0, sizeof(double) * 2 * (size_t)o, st);
-    if (b == 0 || m == 0) return check_launch("fused_sa_backward_prep");
+    cudaMemsetAsync(dbeta_dgamma_wdp, 0, sizeof(double) * 5 * (size_t)o, st);
+    cudaMemsetAsync(a_scatter, 0, sizeof(float) * (size_t)b * n * o, st);
+    if (b == 0 || m == 0) return check_launch("fused_sa_backward_scatter");
     dim3 grid(div_up(m, 32), div_up(o, 32), b);
-    fused_sa_bwd_prep_kernel<<<grid, 256, 0, st>>>(b, m, o, grad_out, out, ysel, mean, invstd, gamma, gy,
-                                                   dbeta_dgamma, dbeta_dgamma + o);
-    return check_launch("fused_sa_backward_prep");
+    fused_sa_bwd_scatter_kernel<<<grid, 256, 0, st>>>(b, n, m, o, nsample, normalize_dp ? 1.0f / radius : 1.0f, grad_out, out,
+                                                      ysel, arg, idx, xyz, new_xyz, mean, invstd, gamma, a_scatter,
+                                                      dbeta_dgamma_wdp, dbeta_dgamma_wdp + o, dbeta_dgamma_wdp + 2 * o);
+    return check_launch("fused_sa_backward_scatter");
 }
 
 extern "C" int amc3d_fused_sa_moments(int b, int n, int m, int nsample, float radius, int normalize_dp,
@@ -833,53 +631,4 @@ extern "C" int amc3d_fused_sa_moments(int b, int n, int m, int nsample, float ra
         fused_sa_moments_kernel<<<(unsigned)div_up_ll(P, 256), 256, 0, st>>>(b, n, m, nsample, normalize_dp ? 1.0f / radius : 1.0f,
                                                                               xyz, new_xyz, idx, cnt, dpsum, mom);
     return check_launch("fused_sa_moments");
-}
-
-template <int NS, bool X3>
-static int launch_fused_dx(const FusedBwdArgs &a, cudaStream_t st) {
-    const size_t smem = 2 * (size_t)(X3 ? 4 : 2) * FS_NT * FS_ROWB + 1024;
-    cudaError_t e = cudaFuncSetAttribute(fused_sa_bwd_dx_kernel<NS, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(fused_sa_bwd_dx_kernel<NS, X3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return (int)e;
-    const long long Q = (long long)a.B * a.M;
-    dim3 grid((unsigned)div_up_ll(Q, FS_NT / NS), (unsigned)div_up(a.C, 128));
-    fused_sa_bwd_dx_kernel<NS, X3><<<grid, FS_THREADS, smem, st>>>(a);
-    return 0;
-}
-
-extern "C" int amc3d_fused_sa_backward_sparse(int b, int n, int m, int c, int o, int o_padded, int nsample, float radius,
-                                              int normalize_dp, int precision, const float *featT, const float *xyz,
-                                              const float *new_xyz, const int *idx, const float *gy,
-                                              const unsigned char *arg, const float *w_t, float *dfeatT,
-                                              float *dw_packed, void *stream) {
-    AMC3D_REQUIRE(b >= 0 && n >= 1 && m >= 0 && c >= 8 && o >= 1, AMC3D_EINVAL, "fused_sa_backward_sparse: bad sizes");
-    AMC3D_REQUIRE(c % 8 == 0 && o % 4 == 0 && o_padded % 32 == 0 && o_padded >= o, AMC3D_ELIMIT,
-                  "fused_sa_backward_sparse: C=%d must be a multiple of 8, O=%d of 4, O_padded=%d of 32", c, o, o_padded);
-    AMC3D_REQUIRE(nsample == 16 || nsample == 32, AMC3D_ELIMIT, "fused_sa_backward_sparse: nsample=%d", nsample);
-    AMC3D_REQUIRE(precision == 1 || precision == 3, AMC3D_EINVAL, "fused_sa_backward_sparse: precision=%d", precision);
-    if (b == 0 || m == 0) return 0;
-    cudaStream_t st = as_stream(stream);
-    FusedBwdArgs a;
-    a.fT = featT; a.xyz = xyz; a.qxyz = new_xyz; a.idx = idx; a.gy = gy; a.arg = arg; a.wT = w_t; a.dfT = dfeatT;
-    a.E = dw_packed; a.B = b; a.N = n; a.M = m; a.C = c; a.O = o; a.Op = o_padded; a.Kp = c + 8;
-    a.inv_radius = normalize_dp ? 1.0f / radius : 1.0f;
-    // sparse weight gradient
-    const int nk = div_up(c + 3, 32), nz = div_up(o, 128);
-    const long long nit = div_up_ll((long long)b * m, FS_NT / nsample);
-    long long chunks = max(1ll, min(nit / 4, (long long)(8 * kNumSMs) / ((long long)nk * nz)));
-    chunks = min(chunks, 65535ll);
-    a.qchunk = (int)div_up_ll(nit, chunks);
-    dim3 wgrid(nk, (unsigned)div_up_ll(nit, a.qchunk), nz);
-    if (nsample == 32) fused_sa_bwd_dw_kernel<32><<<wgrid, 128, 0, st>>>(a);
-    else fused_sa_bwd_dw_kernel<16><<<wgrid, 128, 0, st>>>(a);
-    // sparse input gradient, scatter-added into dfeatT
-    int rc;
-    if (nsample == 32) rc = precision == 3 ? launch_fused_dx<32, true>(a, st) : launch_fused_dx<32, false>(a, st);
-    else rc = precision == 3 ? launch_fused_dx<16, true>(a, st) : launch_fused_dx<16, false>(a, st);
-    if (rc != 0) {
-        set_error("fused_sa_backward_sparse: %s", cudaGetErrorString((cudaError_t)rc));
-        return rc;
-    }
-    return check_launch("fused_sa_backward_sparse");
 }

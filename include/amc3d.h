@@ -180,28 +180,25 @@ int amc3d_fused_sa_forward(int b, int n, int m, int c, int o, int nsample, float
                            const float *gamma, const float *beta, float *ysel, unsigned char *arg,
                            double *sums, float *mean, float *var, float *invstd, float *out, void *stream);
 
-/* Backward of amc3d_fused_sa_forward, in three device steps around a few small library GEMMs on the host
- * side (amcontrast3d_b200/layers/_fused_backward.py has the algebra; csrc/fused_sa.cu the derivation):
- *  _backward_prep    gy (B*M,O) = grad_out * [out > 0] * gamma * invstd, transposed to query-major;
- *                    dbeta_dgamma (2*O) f64 = [sum D, sum D * yhat]
- *  _moments          per support point cnt (B,N) f32 and dpsum (B,N,3) f32 (how often / with which relative
- *                    coordinates it is grouped) and mom (12) f64 = [sum dp (3) | sum dp dp^T (9)]: with these
- *                    the dense BatchNorm terms of the gradient reduce to (B*N) x C x C GEMMs
- *  _backward_sparse  the arg-max terms: dw_packed (O, C+8) += sum_q gy[q,o] * x[arg-max row]  (zeroed by the
- *                    caller) and dfeatT (B,N,C) += scatter-add of  sum_o dY[p,o] W'[o,:]  (tcgen05, dY built
- *                    on the fly; holds the dense terms on entry).  w_t (C, o_padded) = W'[:, :C]^T, zero padded
- *                    to o_padded = O rounded up to 32. */
-int amc3d_fused_sa_backward_prep(int b, int m, int o, const float *grad_out, const float *out,
-                                 const float *ysel, const float *mean, const float *invstd,
-                                 const float *gamma, float *gy, double *dbeta_dgamma, void *stream);
+/* Backward of amc3d_fused_sa_forward: two device steps around a few small library GEMMs on the host side
+ * (amcontrast3d_b200/layers/_fused_backward.py has the algebra; csrc/fused_sa.cu the derivation).
+ *  _backward_scatter  G' = grad_out * [out > 0]; dbeta_dgamma_wdp (5*O) f64 = [sum G' | sum G' yhat | dW of the
+ *                     three relative-coordinate columns (O,3)]; and a_scatter (B*N, O) f32:
+ *                     A[n,o] = sum over the queries whose arg-max sample of channel o is support point n of
+ *                     gamma_o invstd_o G'[q,o].  Then dW_f = A^T f and df = A W_f are (B*N) x O x C GEMMs,
+ *                     1/nsample of the convolution's work.  Zeroes its outputs itself.
+ *  _moments           per support point cnt (B,N) f32 and dpsum (B,N,3) f32 (how often / with which relative
+ *                     coordinates it is grouped) and mom (12) f64 = [sum dp (3) | sum dp dp^T (9)]: with these
+ *                     the dense BatchNorm terms of the gradient reduce to (B*N) x C x C GEMMs. */
+int amc3d_fused_sa_backward_scatter(int b, int n, int m, int o, int nsample, float radius, int normalize_dp,
+                                    const float *grad_out, const float *out, const float *ysel,
+                                    const unsigned char *arg, const int *idx, const float *xyz,
+                                    const float *new_xyz, const float *mean, const float *invstd,
+                                    const float *gamma, float *a_scatter, double *dbeta_dgamma_wdp,
+                                    void *stream);
 int amc3d_fused_sa_moments(int b, int n, int m, int nsample, float radius, int normalize_dp,
                            const float *xyz, const float *new_xyz, const int *idx, float *cnt,
                            float *dpsum, double *mom, void *stream);
-int amc3d_fused_sa_backward_sparse(int b, int n, int m, int c, int o, int o_padded, int nsample, float radius,
-                                   int normalize_dp, int precision, const float *featT, const float *xyz,
-                                   const float *new_xyz, const int *idx, const float *gy,
-                                   const unsigned char *arg, const float *w_t, float *dfeatT,
-                                   float *dw_packed, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * pointops family: packed (n,3) xyz / (n,c) features with cumulative i32 `offset` ends
