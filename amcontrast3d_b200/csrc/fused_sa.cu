@@ -27,9 +27,13 @@ namespace amc3d {
 
 constexpr int FS_NT = 128;                 // grouped positions per CTA (UMMA N)
 constexpr int FS_ROWB = 128;               // bytes per tile row = one swizzle span = 32 floats of K
-constexpr int FS_PROD = 128;               // producer / epilogue threads (warps 0-3); warp 4 issues the MMAs
-constexpr int FS_THREADS = FS_PROD + 32;
-constexpr int FS_MAX_STAGES = 4;
+constexpr int FS_PW = 8;                   // producer warps (0 .. FS_PW-1); warp FS_PW issues the MMAs; then 4 epilogue warps
+constexpr int FS_PROD = FS_PW * 32;        // producer threads
+constexpr int FS_EPI = 256;                // epilogue threads: two per TMEM lane (each takes every other query of the tile)
+constexpr int FS_RPP = FS_PROD / 8;        // tile rows filled per pass (8 lanes per 128-byte row)
+constexpr int FS_NPASS = FS_NT / FS_RPP;   // passes per 128-row tile
+constexpr int FS_THREADS = FS_PROD + 32 + FS_EPI;
+constexpr int FS_MAX_STAGES = 6;
 constexpr int FS_REPL = 64;                // replicas of the BatchNorm sums (spreads the atomics over 64x the cache lines)
 
 __device__ __forceinline__ uint32_t fs_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -154,42 +158,59 @@ struct FusedFwdArgs {
     const float *gamma;     // (O) BatchNorm weight: its sign selects max or min
     float *ysel;            // (B*M, O) pre-normalisation extreme of y over the neighbourhood
     unsigned char *arg;     // (B*M, O) sample index of that extreme (first one)
-    double *gsum, *gsumsq;  // (O) sum y, sum y^2 over all B*M*NS positions (zeroed by the caller)
-    int B, N, M, C, O, Kp, oc, stages;
+    double *gsum, *gsumsq;  // FS_REPL x (O) sum y, sum y^2 over all B*M*NS positions (zeroed by the caller)
+    int B, N, M, C, O, Kp;
+    int stages;             // shared-memory ring depth (2..FS_MAX_STAGES)
+    int fence_mode;         // 0: producers fence (generic -> async proxy) before arriving; 1: the MMA thread fences after the wait;
+                            // 2: as 1, and the arrival itself is asynchronous (cp.async.mbarrier.arrive.noinc)
+    int w_resident;         // 1: the whole (128 x Kp) weight slice stays in shared memory for the CTA's lifetime
+    int nslices;            // ceil(O / 128): output-channel slices per position tile
+    long long nitems;       // position tiles x slices
     float inv_radius;       // 1/radius with normalize_dp, else 1
 };
 
+// Persistent, warp-specialised:  warps 0-7 PRODUCE the operand tiles (ring of `stages` buffers), warp 8 ISSUES the
+// MMAs into one of two TMEM accumulators, warps 9-16 run the EPILOGUE of the previous work item out of the other
+// accumulator.  A work item = (tile of 128 grouped positions, slice of 128 output channels); a CTA takes items
+// blockIdx.x, blockIdx.x + gridDim.x, ...  Barriers: full[s] / empty[s] per ring slot (producers <-> MMA),
+// acc_full[b] / acc_empty[b] per accumulator (MMA <-> epilogue), w_full for the resident weight slice.
 template <int NS, bool X3>
-__global__ void __launch_bounds__(FS_THREADS, 3)
+__global__ void __launch_bounds__(FS_THREADS, 1)
 fused_sa_fwd_kernel(const FusedFwdArgs a) {
     constexpr int QPT = FS_NT / NS;                       // queries per tile
+    constexpr uint32_t T_BYTES = (X3 ? 2u : 1u) * FS_NT * FS_ROWB;     // one operand tile (hi [+ lo]): 128 rows x 128 B
     extern __shared__ __align__(1024) unsigned char fs_smem_raw[];
     // the runtime only guarantees 16-byte alignment of dynamic shared memory: align by hand
     unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(fs_smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int oc = a.oc;                                  // output channels of this CTA (128 / 256 / 512)
-    const uint32_t x_bytes = FS_NT * FS_ROWB, w_bytes = (uint32_t)oc * FS_ROWB;
-    const uint32_t stage_bytes = (X3 ? 2u : 1u) * (x_bytes + w_bytes);
-    __shared__ __align__(8) uint64_t bars[2 * FS_MAX_STAGES + 1];
-    const int FS_STAGES = a.stages;
+    __shared__ __align__(8) uint64_t bars[2 * FS_MAX_STAGES + 5];
     __shared__ uint32_t tmem_base_s;
+    const int S = a.stages;
+    const int nchunks = (a.Kp + 31) / 32;
+    const bool wres = a.w_resident != 0;
+    // layout: [resident W: nchunks tiles] then the ring; a ring slot is [X tile] or [X tile | W tile]
+    unsigned char *ring = base + (wres ? (size_t)nchunks * T_BYTES : 0);
+    const uint32_t slot_bytes = wres ? T_BYTES : 2 * T_BYTES;
+    uint64_t *full = bars, *empty = bars + FS_MAX_STAGES, *acc_full = bars + 2 * FS_MAX_STAGES,
+             *acc_empty = bars + 2 * FS_MAX_STAGES + 2, *w_full = bars + 2 * FS_MAX_STAGES + 4;
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const long long Q = (long long)a.B * a.M;
-    const long long q0 = (long long)blockIdx.x * QPT;
-    const int o0 = blockIdx.y * oc;
-    const int nchunks = (a.Kp + 31) / 32;
 
     if (tid == 0) {
-        for (int s = 0; s < FS_STAGES; ++s) {
-            mbar_init(fs_smem(&bars[s]), FS_PROD);                 // full[s]: every producer thread arrives
-            mbar_init(fs_smem(&bars[FS_STAGES + s]), 1);           // empty[s]: one tcgen05.commit
+        for (int s = 0; s < FS_MAX_STAGES; ++s) {
+            mbar_init(fs_smem(&full[s]), FS_PROD);                 // every producer thread arrives
+            mbar_init(fs_smem(&empty[s]), 1);                      // one tcgen05.commit
         }
-        mbar_init(fs_smem(&bars[2 * FS_STAGES]), 1);               // accumulators complete
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(fs_smem(&acc_full[b]), 1);                   // one tcgen05.commit
+            mbar_init(fs_smem(&acc_empty[b]), FS_EPI);             // every epilogue thread arrives
+        }
+        mbar_init(fs_smem(w_full), FS_PROD);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {                                               // TMEM: oc columns (128 lanes x oc x f32)
+    if (warp == FS_PW) {                                           // TMEM: two accumulators of 128 lanes x 128 columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(fs_smem(&tmem_base_s)),
-                     "r"((uint32_t)oc)
+                     "r"(256u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -198,173 +219,242 @@ fused_sa_fwd_kernel(const FusedFwdArgs a) {
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-    if (warp < 4) {
-        // ------------------------------------------------------------------ producers
-        const int slot = tid & 7, rsub = tid >> 3;                 // 8 lanes per 128-byte row, 16 rows per pass
-        // the 8 grouped positions this thread fetches: row r = i*16 + rsub -> (query, sample) -> support row
-        long long frow[FS_NT / 16];                                // (b*N + n) * C, or -1 past the end
-        int qof[FS_NT / 16];                                       // query index (for the relative coordinates)
+    if (warp < FS_PW) {
+        // ================================================================== producers
+        const int slot = tid & 7, rsub = tid >> 3;                 // 8 lanes per 128-byte row, FS_RPP rows per pass
+        // neighbour index of the grouped positions this thread fetches in an item (raw loads: nothing may depend on
+        // them until the item starts, so that they are in flight during the previous item's chunks)
+        auto load_meta = [&](long long item, int (&nidx)[FS_NPASS]) {
+            const long long q0 = (item / a.nslices) * QPT;
 #pragma unroll
-        for (int i = 0; i < FS_NT / 16; ++i) {
-            const int r = i * 16 + rsub;
-            const long long qg = q0 + r / NS;
-            frow[i] = -1;
-            qof[i] = 0;
-            if (qg < Q) {
-                const int n = __ldg(a.idx + qg * NS + (r % NS));
-                const long long b = qg / a.M;
-                frow[i] = (b * a.N + n);
-                qof[i] = (int)(qg - q0);
+            for (int i = 0; i < FS_NPASS; ++i) {
+                const int r = i * FS_RPP + rsub;
+                const long long qg = q0 + r / NS;
+                nidx[i] = qg < Q ? __ldg(a.idx + qg * NS + (r % NS)) : 0;
             }
-        }
-        // fill stage `st` with K chunk `kc`.  ASYNC (TF32 mode): 16-byte cp.async copies straight into the swizzled
-        // tile — no registers, so several chunks are in flight per thread; otherwise through registers (the 3xTF32
-        // split needs the values).
-        auto fill = [&](int kc, auto async_tag) {
-            constexpr bool ASYNC = decltype(async_tag)::value;
-            const int st = kc % FS_STAGES;
-            if (kc >= FS_STAGES) mbar_wait(fs_smem(&bars[FS_STAGES + st]), (uint32_t)((kc / FS_STAGES - 1) & 1));
-            unsigned char *xs = base + (size_t)st * stage_bytes;
-            unsigned char *xl = xs + x_bytes;                      // X3 only
-            unsigned char *ws = xs + (X3 ? 2u : 1u) * x_bytes;
-            unsigned char *wl = ws + w_bytes;                      // X3 only
-            const int k0 = kc * 32 + slot * 4;
-            // X: gathered neighbour rows | relative coordinates | zeros
+        };
+        // support row (b*N + n) per position, -1 past the end
+        auto rows_of = [&](long long item, const int (&nidx)[FS_NPASS], long long (&frow)[FS_NPASS]) {
+            const long long q0 = (item / a.nslices) * QPT;
 #pragma unroll
-            for (int i = 0; i < FS_NT / 16; ++i) {
-                const int r = i * 16 + rsub;
-                const bool feat = frow[i] >= 0 && k0 + 4 <= a.C;
-                if (ASYNC && !(frow[i] >= 0 && k0 == a.C)) {
-                    cp_async16(fs_smem(xs) + sw128_off(r, slot), feat ? a.fT + frow[i] * a.C + k0 : a.fT, feat);
+            for (int i = 0; i < FS_NPASS; ++i) {
+                const long long qg = q0 + (i * FS_RPP + rsub) / NS;
+                frow[i] = qg < Q ? (qg / a.M) * a.N + nidx[i] : -1;
+            }
+        };
+        auto fill_w = [&](unsigned char *wt, int o0, int kc, auto async_tag) {
+            constexpr bool ASYNC = decltype(async_tag)::value;
+            const int k0 = kc * 32 + slot * 4;
+#pragma unroll
+            for (int i = 0; i < FS_NPASS; ++i) {
+                const int r = i * FS_RPP + rsub;
+                const int o = o0 + r;
+                const bool ok = o < a.O && k0 < a.Kp;
+                if (ASYNC) {
+                    cp_async16(fs_smem(wt) + sw128_off(r, slot), ok ? a.Wp + (long long)o * a.Kp + k0 : a.Wp, ok);
+                } else {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok) v = __ldg(reinterpret_cast<const float4 *>(a.Wp + (long long)o * a.Kp + k0));
+                    fs_store<X3>(wt, wt + FS_NT * FS_ROWB, sw128_off(r, slot), v);
+                }
+            }
+        };
+        auto fill_x = [&](unsigned char *xt, long long item, const long long (&frow)[FS_NPASS], int kc, auto async_tag) {
+            constexpr bool ASYNC = decltype(async_tag)::value;
+            const long long q0 = (item / a.nslices) * QPT;
+            const int k0 = kc * 32 + slot * 4;
+#pragma unroll
+            for (int i = 0; i < FS_NPASS; ++i) {
+                const int r = i * FS_RPP + rsub;
+                const bool live = frow[i] >= 0;
+                const bool feat = live && k0 + 4 <= a.C;
+                const bool isdp = live && k0 == a.C;
+                if (ASYNC && !isdp) {
+                    cp_async16(fs_smem(xt) + sw128_off(r, slot), feat ? a.fT + frow[i] * a.C + k0 : a.fT, feat);
                     continue;
                 }
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (feat) {
                     v = __ldg(reinterpret_cast<const float4 *>(a.fT + frow[i] * a.C + k0));
-                } else if (frow[i] >= 0 && k0 == a.C) {
+                } else if (isdp) {
                     const float *pp = a.xyz + frow[i] * 3;
-                    const float *qq = a.qxyz + (q0 + qof[i]) * 3;
+                    const float *qq = a.qxyz + (q0 + r / NS) * 3;
                     v.x = (__ldg(pp) - __ldg(qq)) * a.inv_radius;
                     v.y = (__ldg(pp + 1) - __ldg(qq + 1)) * a.inv_radius;
                     v.z = (__ldg(pp + 2) - __ldg(qq + 2)) * a.inv_radius;
                 }
-                fs_store<X3>(xs, xl, sw128_off(r, slot), v);
-            }
-            // W': rows o0 .. o0+oc
-            for (int i = 0; i < oc / 16; ++i) {
-                const int r = i * 16 + rsub;
-                const int o = o0 + r;
-                const bool ok = o < a.O && k0 < a.Kp;
-                if (ASYNC) {
-                    cp_async16(fs_smem(ws) + sw128_off(r, slot), ok ? a.Wp + (long long)o * a.Kp + k0 : a.Wp, ok);
-                } else {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ok) v = __ldg(reinterpret_cast<const float4 *>(a.Wp + (long long)o * a.Kp + k0));
-                    fs_store<X3>(ws, wl, sw128_off(r, slot), v);
-                }
+                fs_store<X3>(xt, xt + FS_NT * FS_ROWB, sw128_off(r, slot), v);
             }
         };
-        if (!X3) {
-            // software pipeline: the copies of chunk kc + STAGES - 1 are issued before chunk kc is handed to the MMA
-            for (int kc = 0; kc < FS_STAGES - 1; ++kc) {
-                if (kc < nchunks) fill(kc, std::true_type{});
-                asm volatile("cp.async.commit_group;" ::: "memory");
+        using Async = std::integral_constant<bool, !X3>;           // TF32: cp.async ring; 3xTF32: through registers
+        // hand chunk `c` (global chunk counter) to the MMA warp
+        auto publish = [&](long long c) {
+            if (a.fence_mode == 0) fence_async_smem();             // generic-proxy writes -> visible to the MMA (async proxy)
+            mbar_arrive(fs_smem(&full[c % S]));
+        };
+        auto wait_groups = [&](int n) {                            // cp.async.wait_group needs an immediate
+            switch (n) {
+                case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+                case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+                case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+                case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+                case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+                default: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
             }
-            for (int kc = 0; kc < nchunks; ++kc) {
-                if (kc + FS_STAGES - 1 < nchunks) fill(kc + FS_STAGES - 1, std::true_type{});
+        };
+        if (wres) {                                                // the weight slice, once (a.nslices == 1)
+            for (int kc = 0; kc < nchunks; ++kc) fill_w(base + (size_t)kc * T_BYTES, 0, kc, Async{});
+            if (!X3) {
                 asm volatile("cp.async.commit_group;" ::: "memory");
-                // all but the newest STAGES-1 groups are complete -> chunk kc has landed (this thread's part)
-                if (FS_STAGES == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
-                else if (FS_STAGES == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
-                else asm volatile("cp.async.wait_group 3;" ::: "memory");
-                fence_async_smem();                                // generic-proxy writes -> visible to the MMA (async proxy)
-                mbar_arrive(fs_smem(&bars[kc % FS_STAGES]));
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
             }
-        } else {
-            for (int kc = 0; kc < nchunks; ++kc) {
-                fill(kc, std::false_type{});
-                fence_async_smem();
-                mbar_arrive(fs_smem(&bars[kc % FS_STAGES]));
+            fence_async_smem();
+            mbar_arrive(fs_smem(w_full));
+        }
+        long long cur[FS_NPASS];
+        int nxt[FS_NPASS];
+        long long c = 0;                                           // chunks issued so far
+        if ((long long)blockIdx.x < a.nitems) load_meta(blockIdx.x, nxt);
+        for (long long item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+            rows_of(item, nxt, cur);
+            if (item + gridDim.x < a.nitems) load_meta(item + gridDim.x, nxt);     // in flight during this item's chunks
+            const int o0 = (int)(item % a.nslices) * 128;
+            for (int kc = 0; kc < nchunks; ++kc, ++c) {
+                const int st = (int)(c % S);
+                if (c >= S) mbar_wait(fs_smem(&empty[st]), (uint32_t)((c / S - 1) & 1));
+                unsigned char *xt = ring + (size_t)st * slot_bytes;
+                fill_x(xt, item, cur, kc, Async{});
+                if (!wres) fill_w(xt + T_BYTES, o0, kc, Async{});
+                if (!X3 && a.fence_mode == 2) {
+                    // the barrier arrival fires when this thread's copies of the chunk have landed: nothing to wait for
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(fs_smem(&full[st])) : "memory");
+                } else if (!X3) {
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    if (c >= S - 1) {                              // all but the newest S-1 groups have landed
+                        wait_groups(S - 1);
+                        publish(c - (S - 1));
+                    }
+                } else {
+                    publish(c);
+                }
             }
         }
-
-        // ------------------------------------------------------------------ epilogue: this thread owns channel lane `tid`
-        mbar_wait(fs_smem(&bars[2 * FS_STAGES]), 0);
-        tc_fence_after();
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-        for (int j = 0; j < oc / 128; ++j) {
-            const int o = o0 + j * 128 + tid;
-            const bool live = o < a.O;
-            const bool want_max = live ? (__ldg(a.gamma + o) >= 0.f) : true;
-            float csum = 0.f, csq = 0.f;
-#pragma unroll 1
-            for (int qi = 0; qi < QPT; ++qi) {
-                float v[NS];
-                __syncwarp();                                      // .sync.aligned: reconverge after the `continue` below
-                tmem_ld_query<NS>(lane_addr + (uint32_t)(j * 128 + qi * NS), v);    // all lanes of the warp take part
-                const long long qg = q0 + qi;
-                if (!live || qg >= Q) continue;
-                float best = v[0];
-                int bi = 0;
-                float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-                for (int s = 0; s < NS; ++s) {
-                    s1 += v[s];
-                    s2 = fmaf(v[s], v[s], s2);
-                    const bool better = want_max ? (v[s] > best) : (v[s] < best);
-                    if (better) { best = v[s]; bi = s; }
+        if (!X3 && a.fence_mode != 2) {                            // drain the ring
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            for (long long d = (c >= S - 1 ? c - (S - 1) : 0); d < c; ++d) publish(d);
+        }
+    } else if (warp == FS_PW) {
+        // ================================================================== MMA issuer (one elected lane)
+        const uint32_t idesc = umma_idesc_tf32(128, FS_NT);
+        if (wres) {
+            mbar_wait(fs_smem(w_full), 0);
+            tc_fence_after();
+        }
+        long long c = 0, it = 0;
+        for (long long item = blockIdx.x; item < a.nitems; item += gridDim.x, ++it) {
+            const int buf = (int)(it & 1);
+            mbar_wait(fs_smem(&acc_empty[buf]), (uint32_t)(((it >> 1) & 1) ^ 1));   // the epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t d = tmem_base + (uint32_t)(buf * 128);
+            for (int kc = 0; kc < nchunks; ++kc, ++c) {
+                const int st = (int)(c % S);
+                mbar_wait(fs_smem(&full[st]), (uint32_t)((c / S) & 1));
+                if (a.fence_mode != 0) fence_async_smem();
+                tc_fence_after();
+                if ((tid & 31) == 0) {
+                    const uint32_t xs = fs_smem(ring + (size_t)st * slot_bytes);
+                    const uint32_t ws = wres ? fs_smem(base + (size_t)kc * T_BYTES) : xs + T_BYTES;
+                    const uint32_t xl = xs + FS_NT * FS_ROWB, wl = ws + FS_NT * FS_ROWB;     // X3 only
+                    const int ksteps = min(4, (a.Kp - kc * 32) / 8);
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint32_t acc = (kc > 0 || ks > 0) ? 1u : 0u;
+                        const uint64_t da = umma_desc_sw128(ws + ks * 32), db = umma_desc_sw128(xs + ks * 32);
+                        if (X3) {
+                            umma_tf32(d, umma_desc_sw128(wl + ks * 32), db, idesc, acc);    // lo * hi
+                            umma_tf32(d, da, umma_desc_sw128(xl + ks * 32), idesc, 1u);     // hi * lo
+                            umma_tf32(d, da, db, idesc, 1u);                                 // hi * hi
+                        } else {
+                            umma_tf32(d, da, db, idesc, acc);
+                        }
+                    }
+                    umma_commit(fs_smem(&empty[st]));               // frees the ring slot once these MMAs have read it
+                    if (kc == nchunks - 1) umma_commit(fs_smem(&acc_full[buf]));
                 }
-                csum += s1;
-                csq += s2;
-                a.ysel[qg * a.O + o] = best;
-                a.arg[qg * a.O + o] = (unsigned char)bi;
-            }
-            if (live) {
-                const long long rep = (long long)(blockIdx.x % FS_REPL) * 2 * a.O;
-                atomicAdd(a.gsum + rep + o, (double)csum);
-                atomicAdd(a.gsumsq + rep + o, (double)csq);
+                __syncwarp();
             }
         }
         tc_fence_before();
     } else {
-        // ------------------------------------------------------------------ MMA issuer (one elected lane)
-        const uint32_t idesc = umma_idesc_tf32(128, FS_NT);
-        for (int kc = 0; kc < nchunks; ++kc) {
-            const int st = kc % FS_STAGES;
-            mbar_wait(fs_smem(&bars[st]), (uint32_t)((kc / FS_STAGES) & 1));
-            tc_fence_after();
-            if ((tid & 31) == 0) {
-                const uint32_t xs = fs_smem(base + (size_t)st * stage_bytes);
-                const uint32_t xl = xs + x_bytes;
-                const uint32_t ws = xs + (X3 ? 2u : 1u) * x_bytes;
-                const uint32_t wl = ws + w_bytes;
-                const int ksteps = min(4, (a.Kp - kc * 32) / 8);
-                for (int j = 0; j < oc / 128; ++j) {
-                    const uint32_t d = tmem_base + (uint32_t)(j * 128);
-                    const uint32_t wrow = (uint32_t)(j * 128 * FS_ROWB);
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        const uint32_t first = (kc > 0 || ks > 0) ? 1u : 0u;
-                        const uint64_t da = umma_desc_sw128(ws + wrow + ks * 32), db = umma_desc_sw128(xs + ks * 32);
-                        if (X3) {
-                            umma_tf32(d, umma_desc_sw128(wl + wrow + ks * 32), db, idesc, first);   // lo * hi
-                            umma_tf32(d, da, umma_desc_sw128(xl + ks * 32), idesc, 1u);             // hi * lo
-                            umma_tf32(d, da, db, idesc, 1u);                                         // hi * hi
-                        } else {
-                            umma_tf32(d, da, db, idesc, first);
-                        }
-                    }
-                }
-                umma_commit(fs_smem(&bars[FS_STAGES + st]));        // frees the stage once these MMAs have read it
-                if (kc == nchunks - 1) umma_commit(fs_smem(&bars[2 * FS_STAGES]));
+        // ================================================================== epilogue: a thread owns one channel lane and
+        // every other query of the tile (two threads per lane)
+        const int quad = warp & 3;                                 // TMEM lane quadrant this warp may read
+        const int half = (warp - (FS_PW + 1)) >> 2;                // which queries of the tile: qi % 2 == half
+        const int lane_o = quad * 32 + (tid & 31);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        float csum = 0.f, csq = 0.f;                               // BatchNorm sums of channel `co`, flushed when it changes
+        int co = -1;
+        auto flush = [&]() {
+            if (co >= 0 && co < a.O) {
+                const long long rep = (long long)((blockIdx.x * 2 + half) % FS_REPL) * 2 * a.O;
+                atomicAdd(a.gsum + rep + co, (double)csum);
+                atomicAdd(a.gsumsq + rep + co, (double)csq);
             }
-            __syncwarp();
+            csum = 0.f;
+            csq = 0.f;
+        };
+        long long it = 0;
+        for (long long item = blockIdx.x; item < a.nitems; item += gridDim.x, ++it) {
+            const int buf = (int)(it & 1);
+            const long long q0 = (item / a.nslices) * QPT;
+            const int o = (int)(item % a.nslices) * 128 + lane_o;
+            if (o != co) { flush(); co = o; }
+            const bool live = o < a.O;
+            // gamma < 0: BatchNorm + ReLU decrease in y, the pooled maximum sits at the MINIMUM of y: track max of -y
+            const float sgn = (live && __ldg(a.gamma + o) < 0.f) ? -1.f : 1.f;
+            mbar_wait(fs_smem(&acc_full[buf]), (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+#pragma unroll 1
+            for (int qi = half; qi < QPT; qi += 2) {
+                float v[NS];
+                tmem_ld_query<NS>(lane_addr + (uint32_t)(buf * 128 + qi * NS), v);   // warp-uniform control flow up to here
+                // two independent (max, arg-max) chains over the halves, four partial sums: no branches, short chains
+                float m0 = v[0] * sgn, m1 = v[NS / 2] * sgn;
+                int i0 = 0, i1 = NS / 2;
+                float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+#pragma unroll
+                for (int s = 0; s < NS / 2; ++s) {
+                    const float x = v[s], y = v[s + NS / 2];
+                    s1a += x;
+                    s1b += y;
+                    s2a = fmaf(x, x, s2a);
+                    s2b = fmaf(y, y, s2b);
+                    const float tx = x * sgn, ty = y * sgn;
+                    const bool gx = tx > m0, gy = ty > m1;
+                    m0 = gx ? tx : m0;
+                    i0 = gx ? s : i0;
+                    m1 = gy ? ty : m1;
+                    i1 = gy ? s + NS / 2 : i1;
+                }
+                const bool g2 = m1 > m0;                           // ties keep the lower sample index
+                const float best = (g2 ? m1 : m0) * sgn;
+                const int bi = g2 ? i1 : i0;
+                const long long qg = q0 + qi;
+                if (live && qg < Q) {
+                    csum += s1a + s1b;
+                    csq += s2a + s2b;
+                    a.ysel[qg * a.O + o] = best;
+                    a.arg[qg * a.O + o] = (unsigned char)bi;
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(fs_smem(&acc_empty[buf]));                 // the MMA warp may overwrite this accumulator
         }
-        tc_fence_before();
+        flush();
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == FS_PW) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)oc) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
     }
 }
 
@@ -414,16 +504,28 @@ fused_sa_finalize_kernel(int B, int M, int O, const float *__restrict__ ysel, co
 }
 
 template <int NS, bool X3>
-static int launch_fused_fwd(const FusedFwdArgs &a, cudaStream_t st) {
-    const size_t smem = (size_t)a.stages * (X3 ? 2 : 1) * (FS_NT * FS_ROWB + (size_t)a.oc * FS_ROWB) + 1024;
+static int launch_fused_fwd(FusedFwdArgs &a, cudaStream_t st) {
+    static const int env_st = getenv("AMC3D_FUSED_STAGES") ? atoi(getenv("AMC3D_FUSED_STAGES")) : 0;
+    static const int env_wres = getenv("AMC3D_FUSED_WRES") ? atoi(getenv("AMC3D_FUSED_WRES")) : 1;
+    static const int env_ctas = getenv("AMC3D_FUSED_CTAS") ? atoi(getenv("AMC3D_FUSED_CTAS")) : 0;
+    static const int env_fence = getenv("AMC3D_FUSED_FENCE") ? atoi(getenv("AMC3D_FUSED_FENCE")) : 0;
+    a.fence_mode = X3 ? min(env_fence, 1) : env_fence;
+    const size_t tile = (size_t)(X3 ? 2 : 1) * FS_NT * FS_ROWB;
+    const size_t budget = 200 * 1024;                               // of the 227 KB a CTA may own: one persistent CTA per SM
+    const int nchunks = (a.Kp + 31) / 32;
+    a.nslices = div_up(a.O, 128);
+    a.nitems = div_up_ll((long long)a.B * a.M, FS_NT / NS) * a.nslices;
+    // a single output-channel slice whose weights leave room for >= 3 ring slots: keep them resident
+    a.w_resident = (env_wres && a.nslices == 1 && nchunks * tile + 3 * tile <= budget) ? 1 : 0;
+    const size_t fixed = a.w_resident ? nchunks * tile : 0, slot = a.w_resident ? tile : 2 * tile;
+    a.stages = (int)min((size_t)FS_MAX_STAGES, (budget - fixed) / slot);
+    if (env_st >= 2 && env_st <= a.stages) a.stages = env_st;
+    if (a.stages < 2) return (int)cudaErrorInvalidConfiguration;
+    const size_t smem = fixed + a.stages * slot + 1024;
     cudaError_t e = cudaFuncSetAttribute(fused_sa_fwd_kernel<NS, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    // several CTAs per SM (the epilogue of one overlaps the main loop of another): ask for the full shared-memory carve-out
-    e = cudaFuncSetAttribute(fused_sa_fwd_kernel<NS, X3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return (int)e;
-    const long long Q = (long long)a.B * a.M;
-    dim3 grid((unsigned)div_up_ll(Q, FS_NT / NS), (unsigned)div_up(a.O, a.oc));
-    fused_sa_fwd_kernel<NS, X3><<<grid, FS_THREADS, smem, st>>>(a);
+    const long long ctas = env_ctas > 0 ? env_ctas : kNumSMs;
+    fused_sa_fwd_kernel<NS, X3><<<(unsigned)min(a.nitems, ctas), FS_THREADS, smem, st>>>(a);
     return 0;
 }
 
@@ -449,19 +551,6 @@ extern "C" int amc3d_fused_sa_forward(int b, int n, int m, int c, int o, int nsa
     a.ysel = ysel; a.arg = arg; a.gsum = sums; a.gsumsq = sums + o;
     a.B = b; a.N = n; a.M = m; a.C = c; a.O = o; a.Kp = c + 8;
     a.inv_radius = normalize_dp ? 1.0f / radius : 1.0f;
-    const int opad = div_up(o, 128) * 128;
-    // output channels per CTA (TMEM columns) and pipeline depth: tunable for measurements
-    static const int env_oc = getenv("AMC3D_FUSED_OC") ? atoi(getenv("AMC3D_FUSED_OC")) : 0;
-    static const int env_st = getenv("AMC3D_FUSED_STAGES") ? atoi(getenv("AMC3D_FUSED_STAGES")) : 0;
-    const int ocmax = precision == 3 ? 256 : 512;                   // shared-memory budget of a stage
-    // 128 channels per CTA measured best (more CTAs per SM beat the reuse of the gathered tile: case table in
-    // profiles/r02_fused.md); AMC3D_FUSED_OC = 256 / 512 widens it
-    a.oc = 128;
-    if (env_oc == 256 || (env_oc == 512 && ocmax == 512)) a.oc = min(env_oc, opad <= 128 ? 128 : (opad <= 256 ? 256 : 512));
-    (void)ocmax;
-    a.stages = 2;
-    if (env_st >= 2 && env_st <= FS_MAX_STAGES) a.stages = env_st;
-    while (a.stages > 2 && (size_t)a.stages * (precision == 3 ? 2 : 1) * (FS_NT * FS_ROWB + (size_t)a.oc * FS_ROWB) + 2048 > 227 * 1024) --a.stages;
     cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)o * FS_REPL, st);
     int rc;
     if (nsample == 32) rc = precision == 3 ? launch_fused_fwd<32, true>(a, st) : launch_fused_fwd<32, false>(a, st);

@@ -372,6 +372,107 @@ def count_evaluated_pairs(replay):
     return per_entry
 
 
+# ------------------------------------------------------------------------------------------
+# the fused grouping -> conv -> BN -> ReLU -> max operator next to the module composition it replaces
+# ------------------------------------------------------------------------------------------
+def xl_layers(batch, points):
+    """the 19 grouped convolutions of PointNeXt-XL at (batch, points): (kind, level, N, M, C_in, C_out, radius)"""
+    from amcontrast3d_b200.replay import XL
+    n, C = [points], [XL["width"]]
+    for l in range(1, 5):
+        n.append(n[-1] // XL["strides"][l])
+        C.append(C[-1] * 2)
+    layers = []
+    for l in range(1, 5):
+        r = XL["radius"] * 2 ** (l - 1)
+        layers.append(("sa", l, n[l - 1], n[l], C[l - 1], C[l], r))
+        layers += [("la", l, n[l], n[l], C[l], C[l], 2 * r)] * (XL["blocks"][l] - 1)
+    return layers
+
+
+def time_fused_operator(replay, dev, iters=3):
+    """Forward + backward of the 19 grouped convolutions of one step (config 2), training-mode BatchNorm:
+    (a) this package's fused operator (layers/fused.py, TF32 operands on tcgen05, no grouped tensor);
+    (b) the composition the reference's modules execute — QueryAndGroup (this package's grouping kernels, i.e.
+        already faster than the reference's), torch.cat, nn.Conv2d 1x1 through cuDNN (TF32 allowed, torch's
+        default), nn.BatchNorm2d, ReLU, max — with torch autograd.  Ball-query indices are shared and not timed."""
+    import torch.nn as nn
+    from amcontrast3d_b200.layers import QueryAndGroup, ball_query
+    from amcontrast3d_b200.layers.fused import fused_group_conv_bn_relu_max
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = True
+    p = replay._fps_chain(replay.d_xyz)
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    work = []
+    flop = 0.0
+    for kind, l, N, M, cin, cout, r in xl_layers(replay.B, replay.N):
+        sup, qry = (p[l - 1], p[l]) if kind == "sa" else (p[l], p[l])
+        idx = ball_query(r, 32, sup, qry)
+        conv = nn.Conv2d(cin + 3, cout, 1, bias=False).to(dev)
+        bn = nn.BatchNorm2d(cout).to(dev)
+        f = torch.randn((replay.B, cin, N), device=dev, generator=g).requires_grad_(True)
+        go = torch.randn((replay.B, cout, M), device=dev, generator=g)
+        work.append((qry, sup, idx, conv, bn, f, go, r))
+        flop += 2.0 * replay.B * M * 32 * (cin + 3) * cout
+    grouper = {}
+
+    def fused_pass(backward):
+        for qry, sup, idx, conv, bn, f, go, r in work:
+            out = fused_group_conv_bn_relu_max(qry, sup, f, idx, conv.weight, bn, r, True, "tf32")
+            if backward:
+                out.backward(go)
+
+    def composed_pass(backward):
+        for qry, sup, idx, conv, bn, f, go, r in work:
+            qg = grouper.setdefault(r, QueryAndGroup(r, 32, normalize_dp=True))
+            dp, fj = qg(qry, sup, f, idx=idx)
+            out = torch.relu(bn(conv(torch.cat([dp, fj], 1)))).max(-1)[0]
+            if backward:
+                out.backward(go)
+
+    def timed(fn, backward):
+        for _ in range(2):
+            fn(backward)
+        for w in work:
+            w[5].grad = None
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn(backward)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    res = {}
+    try:
+        f_fwd, f_all = timed(fused_pass, False), timed(fused_pass, True)
+        c_fwd, c_all = timed(composed_pass, False), timed(composed_pass, True)
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        tf32_peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
+        res = {"layers": len(work), "conv_gflop_fwd": round(flop / 1e9, 1),
+               "fused": {"fwd_ms": round(f_fwd, 3), "fwd_bwd_ms": round(f_all, 3)},
+               "composition": {"fwd_ms": round(c_fwd, 3), "fwd_bwd_ms": round(c_all, 3),
+                               "what": "QueryAndGroup (this package's grouping kernels) + cat + cuDNN Conv2d 1x1 (TF32) + "
+                                       "BatchNorm2d (training) + ReLU + max, torch autograd"},
+               "speedup_fwd": round(c_fwd / f_fwd, 2), "speedup_fwd_bwd": round(c_all / f_all, 2),
+               "fused_fwd_tflops": round(flop / (f_fwd * 1e-3) / 1e12, 1),
+               "tensor_roofline": {"bound": "tensor", "achieved": round(flop / (f_fwd * 1e-3) / 1e12, 1), "peak": tf32_peak,
+                                   "unit": "TFLOP/s", "frac": round(flop / (f_fwd * 1e-3) / 1e12 / tf32_peak, 4),
+                                   "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 runs at half the bf16 rate)",
+                                   "note": "forward only, eager, whole operator (transpose, weight packing, statistics, normalise "
+                                           "included); the backward does 1/16 of these FLOPs by construction"},
+               "grouped_tensor_bytes_avoided_fwd": int(sum(4.0 * replay.B * w[0].shape[1] * 32 * (w[5].shape[1] + 3) for w in work)),
+               "mode": "eager (per-call Python included on both sides), TF32 operands on both sides, 3 iterations after 2 warm-ups"}
+    except Exception as e:                                     # never break the headline line
+        res = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+    torch.backends.cudnn.allow_tf32 = prev
+    del work
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_ours(args):
     from amcontrast3d_b200 import _capi
     from amcontrast3d_b200 import dist as amdist
@@ -595,6 +696,7 @@ def run_ours(args):
         fps_row["us_per_pick"] = round(1e3 * fps_row["ms"] / picks, 4)
         fps_row["picks"] = picks
 
+    fused = time_fused_operator(replay, dev) if world == 1 and not args.no_fused else None
     ref_gpu = None
     if world == 1 and not args.no_cpu and not args.no_ref_gpu:
         ref_gpu = time_ref_gpu(replay, args.k, last_loss)
@@ -630,7 +732,7 @@ def run_ours(args):
                             "against it — the rest of their issue slots is box tests and top-k maintenance, see "
                             "profiles/r02_search_ncu.md for issue-slot utilisation"},
             "kernels": kernels, "kernel_ms_per_step": round(total_ms, 3), "cpu_baseline": cpu_baseline,
-            "ref_gpu": ref_gpu}
+            "ref_gpu": ref_gpu, "fused_operator": fused}
     print(json.dumps(line), flush=True)
     if world > 1:
         tdist.destroy_process_group()
@@ -652,6 +754,7 @@ def main():
     ap.add_argument("--grad-mb", type=float, default=166.3, help="flat gradient all-reduce per step (N>1): PointNeXt-XL FP32 grads")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-CUDA-kernels-on-this-GPU baseline")
+    ap.add_argument("--no-fused", action="store_true", help="skip the fused-operator vs module-composition leg")
     ap.add_argument("--no-prefetch", action="store_true", help="do not pipeline the FPS chain of the next batch into the current step")
     ap.add_argument("--no-graph", action="store_true", help="time the eager (per-call Python) step instead of the CUDA-graph replay")
     args = ap.parse_args()
