@@ -566,15 +566,29 @@ static cudaError_t launch_for_cs(int cs, int nw, int b, int n, int m, int log2bs
     return launch_for_nw<1>(nw, FPS_ARGS);
 }
 
+
+// b clouds of n points each, contiguous; log2bs = log2 of the reference's block size (it fixes the tie order);
+// every index written is local index + ibase + cloud * istride.  Returns 0 or a cudaError_t.
 static int env_int(const char *name, int dflt) {
     const char *e = getenv(name);
     return e ? atoi(e) : dflt;
 }
 
-// b clouds of n points each, contiguous; log2bs = log2 of the reference's block size (it fixes the tie order);
-// every index written is local index + ibase + cloud * istride.  Returns 0 or a cudaError_t.
+int fps_culled_launch(int b, int n, int m, int log2bs, const float *xyz, float *temp, int *idx, int ibase, int istride,
+                      cudaStream_t st);   // knn_grid.cu: exact spatial culling over sorted tiles
+
 int fps_launch(int b, int n, int m, int log2bs, const float *xyz, float *temp, int *idx, int ibase, int istride,
                cudaStream_t st) {
+    // Scenes beyond the cluster kernels (n > 212 992: they keep every point in registers / shared memory) take the
+    // spatially culled kernel — ~4 tile updates per pick whatever n, 2 - 3 us per pick — instead of the all-points
+    // global kernel at the end of this function.  Below that size the cluster kernels are faster (measured:
+    // profiles/r02_fps.md).  AMC3D_FPS_CULLED_MIN moves the crossover.
+    static const int culled_min = env_int("AMC3D_FPS_CULLED_MIN", 212993);
+    if (n >= culled_min && m >= 64) {
+        const int rc = fps_culled_launch(b, n, m, log2bs, xyz, temp, idx, ibase, istride, st);
+        if (rc == 0) return 0;
+        cudaGetLastError();                    // not applicable / failed: the cluster path decides
+    }
     // cluster size and warps per CTA: as much parallelism as pays off (each round costs one
     // exchange regardless); AMC3D_FPS_CS / AMC3D_FPS_NW override the choice for experiments
     static const int env_cs = env_int("AMC3D_FPS_CS", 0), env_nw = env_int("AMC3D_FPS_NW", 0);

@@ -1033,6 +1033,162 @@ static cudaError_t build(Scratch &ws, int nb, int n, int m, const float *xyz, co
     return cudaSuccess;
 }
 
+// ---------------------------------------------------------------------------------------
+// 5. furthest point sampling with exact culling, for scenes too large for the register-resident cluster kernel
+//    (fps.cu): one CTA per scene over the sorted tiles.
+// ---------------------------------------------------------------------------------------
+// A pick can only lower the running distance t[p] of points closer to it than sqrt(t[p]).  Per tile of GT sorted
+// points the CTA keeps the tile's maximum of t (with the reference's tie key and that point's coordinates); a
+// pick skips every tile whose box is farther from it than that maximum — conservatively, lb2 * (1 - 2^-13) > tmax,
+// the same bound as the searches — because none of its points can change; skipped updates would have been
+// t = min(t, d) with d > t, so every t, and with it every pick, is bit-identical to the reference's sequential
+// scan (sampling_gpu.cu:100-216).  Measured: 4.2 tile updates per pick at 40 000 ... 400 000 points — the work
+// per pick no longer grows with n — but a pick is then a chain of three block barriers and two L2 round trips,
+// 1.9 - 2.8 us, which loses to the register-resident cluster kernel (0.2 - 1.5 us per pick) wherever that one
+// fits (n <= 212 992).  It therefore serves the scenes beyond it, in place of the all-points global kernel.
+// Variants measured and dropped: test + update fused per warp without a work list (2.8 us at 64 000 points:
+// the hits of one warp serialise), 4 warps with the boxes in shared memory (3.1 us).
+constexpr int FC_THREADS = 1024;
+constexpr int FC_WARPS = FC_THREADS / 32;
+__device__ unsigned long long g_fc_hits[2];     // debug (AMC3D_FPS_DEBUG): tile updates, picks
+
+__device__ __forceinline__ uint32_t fps_tie_key(int k, int log2bs) {       // lower wins; as fps.cu tie_key
+    const uint32_t low = (uint32_t)k & ((1u << log2bs) - 1u);
+    const uint32_t rev = log2bs == 0 ? 0u : (__brev(low) >> (32 - log2bs));
+    return (rev << 22) | ((uint32_t)k >> log2bs);
+}
+
+template <bool FC_DEBUG>
+__global__ void __launch_bounds__(FC_THREADS)
+fps_culled_kernel(int n, int npad, int ntb, int m, int log2bs, const float *__restrict__ xyz,
+                  const float4 *__restrict__ sp, const float4 *__restrict__ tlo, const float4 *__restrict__ thi,
+                  float *__restrict__ tsort, float *__restrict__ temp, int *__restrict__ idxs, int ibase, int istride) {
+    extern __shared__ __align__(16) unsigned char fc_smem[];
+    float4 *s_tpt = reinterpret_cast<float4 *>(fc_smem);           // per tile: its farthest point {x, y, z, original index}
+    float *s_tmax = reinterpret_cast<float *>(s_tpt + ntb);        //           that point's running distance
+    uint32_t *s_ttie = reinterpret_cast<uint32_t *>(s_tmax + ntb); //           and tie key
+    int *s_work = reinterpret_cast<int *>(s_ttie + ntb);           // tiles the current pick has to update
+    __shared__ uint32_t s_wv[FC_WARPS], s_wt[FC_WARPS];
+    __shared__ int s_wi[FC_WARPS];
+    __shared__ int s_nwork, s_old;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x;
+    xyz += 3ll * b * n;
+    temp += (long long)b * n;
+    idxs += (long long)b * m;
+    sp += (long long)b * npad;
+    tsort += (long long)b * npad;
+    tlo += (long long)b * ntb;
+    thi += (long long)b * ntb;
+    ibase += b * istride;
+    // running distances in sorted order, as the caller initialised them (1e10)
+    for (int i = tid; i < n; i += FC_THREADS) tsort[i] = temp[__float_as_int(sp[i].w)];
+    for (int t = tid; t < ntb; t += FC_THREADS) s_tmax[t] = INFINITY;     // every tile takes part in the first update
+    float px = __ldg(xyz), py = __ldg(xyz + 1), pz = __ldg(xyz + 2);       // first pick: index 0
+    if (tid == 0) {
+        idxs[0] = ibase;
+        s_nwork = 0;
+    }
+    __syncthreads();
+    for (int j = 1; j < m; ++j) {
+        // A. which tiles can change
+        for (int t = tid; t < ntb; t += FC_THREADS) {
+            const float lb = point_box2(px, py, pz, __ldg(tlo + t), __ldg(thi + t));
+            if (!(lb * KG_SAFE > s_tmax[t])) s_work[atomicAdd(&s_nwork, 1)] = t;
+        }
+        __syncthreads();
+        // B. update them, a warp per tile
+        const int nwork = s_nwork;
+        if (FC_DEBUG && tid == 0) {
+            atomicAdd(&g_fc_hits[0], (unsigned long long)nwork);
+            atomicAdd(&g_fc_hits[1], 1ull);
+        }
+        for (int w = warp; w < nwork; w += FC_WARPS) {
+            const int th = s_work[w];
+            uint32_t bv = 0, bt = 0xffffffffu;
+            float4 bp = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < GR; ++r) {
+                const int i = th * GT + r * 32 + lane;
+                if (i < n) {
+                    const float4 p = __ldg(sp + i);
+                    // operand order of the reference: point - last pick (sampling_gpu.cu:147-150)
+                    const float d = dist2_ref(p.x - px, p.y - py, p.z - pz);
+                    const float t2 = fminf(d, tsort[i]);
+                    tsort[i] = t2;
+                    const uint32_t v = __float_as_uint(t2), tk = fps_tie_key(__float_as_int(p.w), log2bs);
+                    if (v > bv || (v == bv && tk < bt)) { bv = v; bt = tk; bp = p; }
+                }
+            }
+            const uint32_t wv = __reduce_max_sync(0xffffffffu, bv);
+            const uint32_t wt = __reduce_min_sync(0xffffffffu, bv == wv ? bt : 0xffffffffu);
+            if (bv == wv && bt == wt) {
+                s_tmax[th] = __uint_as_float(wv);
+                s_ttie[th] = wt;
+                s_tpt[th] = bp;
+            }
+        }
+        __syncthreads();
+        // C. argmax over the tile maxima (value desc, tie key asc)
+        uint32_t bv = 0, bt = 0xffffffffu;
+        int bi = 0;
+        for (int t = tid; t < ntb; t += FC_THREADS) {
+            const uint32_t v = __float_as_uint(s_tmax[t]), tk = s_ttie[t];
+            if (v > bv || (v == bv && tk < bt)) { bv = v; bt = tk; bi = t; }
+        }
+        uint32_t wv = __reduce_max_sync(0xffffffffu, bv);
+        uint32_t wt = __reduce_min_sync(0xffffffffu, bv == wv ? bt : 0xffffffffu);
+        if (bv == wv && bt == wt) { s_wv[warp] = wv; s_wt[warp] = wt; s_wi[warp] = bi; }
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t v = s_wv[lane], t2 = s_wt[lane];
+            wv = __reduce_max_sync(0xffffffffu, v);
+            wt = __reduce_min_sync(0xffffffffu, v == wv ? t2 : 0xffffffffu);
+            if (v == wv && t2 == wt) s_old = s_wi[lane];
+            if (lane == 0) s_nwork = 0;
+        }
+        __syncthreads();
+        const float4 pk = s_tpt[s_old];
+        px = pk.x; py = pk.y; pz = pk.z;
+        if (tid == 0) idxs[j] = __float_as_int(pk.w) + ibase;
+    }
+    __syncthreads();
+    // the caller's temp holds the final running distances, in original order, as the reference leaves them
+    for (int i = tid; i < n; i += FC_THREADS) temp[__float_as_int(sp[i].w)] = tsort[i];
+}
+
+// b scenes of n points; returns 0, a cudaError_t, or -1 when this path does not apply (caller falls back)
+int fps_culled_launch(int b, int n, int m, int log2bs, const float *xyz, float *temp, int *idx, int ibase, int istride,
+                      cudaStream_t st) {
+    if (n > 1000000 || b > 65535) return -1;         // tile state of a scene lives in shared memory (28 B per 128 points)
+    Scratch ws(st);
+    Built B;
+    cudaError_t e = build(ws, b, n, n, xyz, xyz, B);
+    if (e != cudaSuccess) return (int)e;
+    float *tsort = ws.get<float>((size_t)b * B.gs.npad);
+    if (ws.err != cudaSuccess) return (int)ws.err;
+    const size_t smem = 28 * (size_t)B.gs.ntb;
+    if (smem > 40 * 1024) {
+        e = cudaFuncSetAttribute(fps_culled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fps_culled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    static const bool dbg = getenv("AMC3D_FPS_DEBUG") != nullptr;
+    if (dbg) {
+        unsigned long long z[2] = {0, 0}, h[2];
+        cudaMemcpyToSymbol(g_fc_hits, z, sizeof(z));
+        fps_culled_kernel<true><<<b, FC_THREADS, smem, st>>>(n, B.gs.npad, B.gs.ntb, m, log2bs, xyz, B.sp, B.tlo, B.thi, tsort,
+                                                            temp, idx, ibase, istride);
+        cudaStreamSynchronize(st);
+        cudaMemcpyFromSymbol(h, g_fc_hits, sizeof(h));
+        fprintf(stderr, "[fps_culled] n=%d m=%d tiles=%d: %.2f tile updates per pick\n", n, m, B.gs.ntb, (double)h[0] / (double)(h[1] ? h[1] : 1));
+        return (int)cudaGetLastError();
+    }
+    fps_culled_kernel<false><<<b, FC_THREADS, smem, st>>>(n, B.gs.npad, B.gs.ntb, m, log2bs, xyz, B.sp, B.tlo, B.thi, tsort,
+                                                         temp, idx, ibase, istride);
+    return (int)cudaGetLastError();
+}
+
 static void search_grid(const Built &B, int m, int &qpw, int &blocks) {
     // enough warps to fill the machine a few times over; long runs of consecutive queries per warp
     // only when there are plenty of queries

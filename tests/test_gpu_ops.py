@@ -10,11 +10,13 @@ GPU parity of the point-grouping operators against the CPU restatement of the re
 kernels (oracle/ops_oracle.c), called through the reference-facing Python operators, which in
 turn go through the C-ABI of include/amc3d.h.  Bar: bit-exact indices / distances / gathers;
 scatter-add gradients within 1e-5 relative (the reference's own atomics are order-dependent)."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
-from _util import rel_err
+from _util import REPO, rel_err
 from amcontrast3d_b200 import scenes
 from oracle import ops_oracle as oo
 
@@ -156,6 +158,41 @@ def test_fps_large_scenes(n, m):
     ridx, _ = oo.fps(xyz, m)
     idx = furthest_point_sample(_t(xyz), m)
     assert np.array_equal(idx.cpu().numpy(), ridx)
+
+
+@pytest.mark.parametrize("n,m,kind,culled", [(64000, 16000, "surface", False), (50000, 3000, "volume", True),
+                                             (120000, 1500, "surface", True), (230000, 800, "surface", False)])
+def test_fps_long_sequences_and_culled_kernel(n, m, kind, culled, monkeypatch):
+    """long pick sequences (config 3's 64 000 -> 16 000 in full) and the running distances left in `temp`, bit for
+    bit; `culled` forces the spatially culled kernel (knn_grid.cu fps_culled_kernel, the default beyond 212 992
+    points) onto smaller scenes as well"""
+    import subprocess, sys, json
+    if culled:
+        # the crossover is read once per process: run this case in a child with the override
+        code = ("import sys, json, numpy as np, torch; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+                "from amcontrast3d_b200 import scenes, pointnet2_batch_cuda as ext\n"
+                "from oracle import ops_oracle as oo\n"
+                "xyz, _ = scenes.batch_of_scenes(2, %d, %r, first_scene=5)\n"
+                "ridx, rtemp = oo.fps(xyz, %d)\n"
+                "x = torch.from_numpy(xyz).cuda(); temp = torch.full((2, %d), 1e10, device='cuda')\n"
+                "out = torch.zeros((2, %d), dtype=torch.int32, device='cuda')\n"
+                "ext.furthest_point_sampling_wrapper(2, %d, %d, x, temp, out)\n"
+                "print(json.dumps([bool(np.array_equal(out.cpu().numpy(), ridx)), bool(np.array_equal(temp.cpu().numpy(), rtemp))]))\n"
+                % (REPO, os.path.join(REPO, "tests"), n, kind, m, n, m, n, m))
+        env = dict(os.environ, AMC3D_FPS_CULLED_MIN="1000")
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert json.loads(r.stdout.strip().splitlines()[-1]) == [True, True]
+        return
+    from amcontrast3d_b200 import pointnet2_batch_cuda as ext
+    xyz, _ = scenes.batch_of_scenes(2, n, kind, first_scene=5)
+    ridx, rtemp = oo.fps(xyz, m)
+    x = _t(xyz)
+    temp = torch.full((2, n), 1e10, device=DEV)
+    out = torch.zeros((2, m), dtype=torch.int32, device=DEV)
+    ext.furthest_point_sampling_wrapper(2, n, m, x, temp, out)
+    assert np.array_equal(out.cpu().numpy(), ridx)
+    assert np.array_equal(temp.cpu().numpy(), rtemp)
 
 
 @pytest.mark.parametrize("n,m", [(300, 120), (1500, 500), (5000, 700), (24000, 800)])
