@@ -23,6 +23,7 @@
 //   amloss_backward G lanes/row   projection through the normalisation, scaled by
 //                                 upstream/|sel| read from device memory (no host sync)
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace amc3d {
 
@@ -237,7 +238,9 @@ __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, 
                  : "memory");
 }
 
-template <int G, int V>
+// KEC > 0 (V == 1 only): the ke <= KEC neighbour chunks a lane reads for the cosines stay in registers (4 * KEC
+// floats) and feed the gradient pass, so every neighbour row is fetched ONCE; KEC == 0 re-reads them in pass 2.
+template <int G, int V, int KEC = 0>
 __global__ void __launch_bounds__(256)
 amloss_forward_kernel(int m, int ke, int ld, const float *__restrict__ f, const float *__restrict__ inv,
                       const int *__restrict__ nbr, const uint32_t *__restrict__ posbits,
@@ -273,10 +276,13 @@ amloss_forward_kernel(int m, int ke, int ld, const float *__restrict__ f, const 
     for (int v = 0; v < V; ++v) fi[v] = __ldg(reinterpret_cast<const float4 *>(f + ii * D) + v * G + g);
 
     // pass 1: cosine similarities
+    constexpr int KEL = KEC > 0 ? KEC : KE_MAX;       // compile-time bound of the neighbour loops
     float s[KE_MAX];
+    float4 wj[KEC > 0 ? KEC : 1];
 #pragma unroll
-    for (int j = 0; j < KE_MAX; ++j) {
-        s[j] = 0.f;
+    for (int j = 0; j < KE_MAX; ++j) s[j] = 0.f;
+#pragma unroll
+    for (int j = 0; j < KEL; ++j) {
         if (j < ke) {
             const long long nj = __ldg(row + j);
             const float4 *fr = reinterpret_cast<const float4 *>(f + nj * D);
@@ -284,6 +290,7 @@ amloss_forward_kernel(int m, int ke, int ld, const float *__restrict__ f, const 
 #pragma unroll
             for (int v = 0; v < V; ++v) {
                 const float4 w = __ldg(fr + v * G + g);
+                if (KEC > 0) wj[j] = w;
                 acc += fi[v].x * w.x + fi[v].y * w.y + fi[v].z * w.z + fi[v].w * w.w;
             }
             acc = group_sum<G>(acc);
@@ -361,7 +368,7 @@ amloss_forward_kernel(int m, int ke, int ld, const float *__restrict__ f, const 
 #pragma unroll
     for (int v = 0; v < V; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < KE_MAX; ++j) {
+    for (int j = 0; j < KEL; ++j) {
         if (j < ke) {
             const long long nj = __ldg(row + j);
             const float gu = gj[j] * __ldg(inv + nj);   // gj * inv_j  (u_j = f_j * inv_j)
@@ -370,7 +377,7 @@ amloss_forward_kernel(int m, int ke, int ld, const float *__restrict__ f, const 
             float *gr = ghat + nj * D;
 #pragma unroll
             for (int v = 0; v < V; ++v) {
-                const float4 w = __ldg(fr + v * G + g);
+                const float4 w = KEC > 0 ? wj[j] : __ldg(fr + v * G + g);
                 acc[v].x += gu * w.x; acc[v].y += gu * w.y; acc[v].z += gu * w.z; acc[v].w += gu * w.w;
                 if (sel)
                     red_add_v4(gr + (v * G + g) * 4, gi * fi[v].x, gi * fi[v].y, gi * fi[v].z, gi * fi[v].w);
@@ -619,8 +626,23 @@ static void launch_fwd(int m, int ke, int ld, const float *f, const float *inv, 
                        const uint32_t *posbits, const float *a, const amc3d_loss_params &prm,
                        float *loss_pt, float *ghat, const int *order, cudaStream_t st) {
     const long long threads = (long long)m * G;
-    amloss_forward_kernel<G, V><<<(unsigned)div_up_ll(threads, 256), 256, 0, st>>>(m, ke, ld, f, inv, nbr, posbits,
-                                                                                    a, prm, loss_pt, ghat, order);
+    const unsigned blocks = (unsigned)div_up_ll(threads, 256);
+    // The register-cached variants (KEC > 0: every neighbour row fetched once) are built but off: measured at config 2
+    // they LOSE, 0.524 ms against 0.424 ms for the four stages — the second read of a row hits L1 and is cheap,
+    // 122 registers per thread instead of 65 halve the resident warps, and what bounds the kernel is the
+    // neighbour-role reduction traffic into L2 (16 red.v4 per lane and anchor).  AMC3D_AMLOSS_RC=1 enables them.
+    static const bool no_rc = getenv("AMC3D_AMLOSS_RC") == nullptr;
+    if constexpr (V == 1) {
+    if (!no_rc && ke <= 16) {
+        amloss_forward_kernel<G, V, 16><<<blocks, 256, 0, st>>>(m, ke, ld, f, inv, nbr, posbits, a, prm, loss_pt, ghat, order);
+        return;
+    }
+    if (!no_rc && ke <= 24) {
+        amloss_forward_kernel<G, V, 24><<<blocks, 256, 0, st>>>(m, ke, ld, f, inv, nbr, posbits, a, prm, loss_pt, ghat, order);
+        return;
+    }
+    }
+    amloss_forward_kernel<G, V><<<blocks, 256, 0, st>>>(m, ke, ld, f, inv, nbr, posbits, a, prm, loss_pt, ghat, order);
 }
 
 extern "C" int amc3d_amloss_forward(int m, int d, int ke, int ld, const float *f, const float *inv,
