@@ -78,6 +78,7 @@ SIGNATURES = {
     "amc3d_pointops_subtraction_backward": [_I, _I, _I, _P, _P, _P, _P, _P],
     "amc3d_pointops_aggregation_forward": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "amc3d_pointops_aggregation_backward": [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "amc3d_class_counts": [_I, _I, _P, _P, _P, _I, _P, _P],
     "amc3d_stage_labels": [_I, _I, _I, _I, _LL, _P, _P, _P, _P],
     "amc3d_posmask_count": [_I, _I, _I, _P, _P, _P, _P, _P, _P],
     "amc3d_ambiguity": [_I, _I, _I, _P, _P, _P, _P, _P, _I, _F, _F, _P, _P, _P],

@@ -562,9 +562,45 @@ amloss_backward_generic_kernel(int m, int d, const float *__restrict__ f, const 
     }
 }
 
+// per-class confusion counts of a prediction against the labels (what the trainer's ConfusionMatrix.update
+// accumulates and all-reduces every step, main_AA.py:461,496-507): out[0..ncls) = tp, [ncls..2ncls) = #predicted,
+// [2ncls..3ncls) = #labelled.  pred == NULL: the prediction is the label of the point's first listed neighbour
+// (nbr[i*ld]) — the stand-in the path replay uses.  Block-local shared-memory histograms, one float atomic per
+// class and block (exact below 2^24).
+__global__ void __launch_bounds__(256)
+class_counts_kernel(int m, int ncls, const int *__restrict__ target, const int *__restrict__ pred,
+                    const int *__restrict__ nbr, int ld, float *__restrict__ out) {
+    extern __shared__ int s_hist[];
+    for (int i = threadIdx.x; i < 3 * ncls; i += 256) s_hist[i] = 0;
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < m; i += (long long)gridDim.x * 256) {
+        const int t = __ldg(target + i);
+        const int p = pred != nullptr ? __ldg(pred + i) : __ldg(target + __ldg(nbr + i * ld));
+        if (t >= 0 && t < ncls) {
+            atomicAdd(&s_hist[2 * ncls + t], 1);
+            if (p == t) atomicAdd(&s_hist[t], 1);
+        }
+        if (p >= 0 && p < ncls) atomicAdd(&s_hist[ncls + p], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * ncls; i += 256)
+        if (s_hist[i]) atomicAdd(out + i, (float)s_hist[i]);
+}
+
 }  // namespace amc3d
 
 using namespace amc3d;
+
+extern "C" int amc3d_class_counts(int m, int ncls, const int *target, const int *pred, const int *nbr, int ld,
+                                  float *out, void *stream) {
+    AMC3D_REQUIRE(m >= 0 && ncls >= 1 && ncls <= 4096, AMC3D_EINVAL, "class_counts: bad sizes m=%d ncls=%d", m, ncls);
+    AMC3D_REQUIRE(pred != nullptr || (nbr != nullptr && ld >= 1), AMC3D_EINVAL, "class_counts: neither pred nor nbr given");
+    cudaStream_t st = as_stream(stream);
+    cudaMemsetAsync(out, 0, sizeof(float) * 3 * (size_t)ncls, st);
+    if (m > 0)
+        class_counts_kernel<<<min(div_up(m, 256), 2 * kNumSMs), 256, sizeof(int) * 3 * ncls, st>>>(m, ncls, target, pred, nbr, ld, out);
+    return check_launch("class_counts");
+}
 
 extern "C" int amc3d_stage_labels(int m, int kr, int ncls, int has_ignore, long long ignore_index,
                                   const long long *target, const int *nidx, int *cls, void *stream) {

@@ -92,10 +92,18 @@ class GradBuckets:
     (what DDP does for the 41.58 M-parameter PointNeXt-XL: 166.3 MB FP32).
     Buckets are sized for launch latency (NVSwitch makes bandwidth uniform), default 32 MB."""
 
-    def __init__(self, numel: int, device, bucket_mb: float = 32.0):
-        self.flat = torch.zeros(numel, dtype=torch.float32, device=device)
+    def __init__(self, numel: int, device, bucket_mb: float = 32.0, tail_mb: float = 1.0, tail_extra: int = 0):
+        """`tail_mb`: size of the LAST bucket — the one that only becomes ready when the backward ends and whose
+        all-reduce is therefore exposed; DDP makes the corresponding (first-allocated) bucket 1 MB for the same
+        reason.  `tail_extra` floats are appended to it (`self.extra`): the step's packed statistics ride along
+        with the last gradient bucket instead of paying for a collective of their own."""
+        self.flat = torch.zeros(numel + tail_extra, dtype=torch.float32, device=device)
         per = max(1, int(bucket_mb * 1e6 / 4))
-        self.buckets = [self.flat[i:i + per] for i in range(0, numel, per)]
+        tail = min(numel, max(1, int(tail_mb * 1e6 / 4)))
+        body = numel - tail
+        self.buckets = [self.flat[i:min(i + per, body)] for i in range(0, body, per)]
+        self.buckets.append(self.flat[body:])
+        self.extra = self.flat[numel:] if tail_extra else None
         self.stream = torch.cuda.Stream(device=device) if torch.device(device).type == "cuda" else None
         self._work = []
 

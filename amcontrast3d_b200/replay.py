@@ -359,9 +359,35 @@ class PathReplay:
             tensors.append(loss)
             grads.append(None)
         torch.autograd.backward(tensors, grads)
+        if self.stats_sink is not None and loss is not None:
+            self._write_stats(loss)
         if self.prefetch:
             self._rotate_prefetch()
         return loss
+
+    # the step's statistics, as the trainer reduces them across ranks (main_AA.py:461,496-507): packed into ONE
+    # float32 vector [loss_sum, CE, AM, n_selected[4], tp[ncls], union[ncls], count[ncls]] that the caller owns
+    # (bench.py: the tail of the last gradient bucket, so that no separate small all-reduce is exposed after the
+    # step).  Static shapes, no host read: part of the captured graph.
+    stats_sink = None
+
+    def _write_stats(self, loss):
+        ncls = self.num_classes + (1 if self.ignore_index is not None else 0)
+        geo = self._am_geometry
+        n_sel = torch.stack([g["stats"][0] for g in geo]).float()                 # points the loss selected, per stage
+        g0 = geo[0]
+        cls, knn = g0["cls"], g0["knn_idx"]                     # stage-0 labels (ignored -> extra class); kNN rows
+        counts = torch.empty(3 * ncls, dtype=torch.float32, device=cls.device)
+        from . import _capi
+        with _capi.guard(cls):                                  # prediction = the nearest neighbour's label (column 1)
+            _capi.call("amc3d_class_counts", int(cls.shape[0]), ncls, _capi.ptr(cls), 0, knn.data_ptr() + 4,
+                       int(knn.shape[1]), _capi.ptr(counts), _capi.stream(cls))
+        tp, npred, count = counts[:ncls], counts[ncls:2 * ncls], counts[2 * ncls:]
+        union = count + npred - tp
+        lf = loss.detach().float().reshape(1)
+        vec = torch.cat([lf, torch.zeros_like(lf), lf, n_sel, tp[:self.num_classes], union[:self.num_classes],
+                         count[:self.num_classes]])
+        self.stats_sink.copy_(vec)
 
     def step_e2e(self):
         """The same step driven from HOST buffers: pinned xyz/labels -> device, step, loss -> host."""

@@ -489,7 +489,12 @@ def run_ours(args):
     replay = PathReplay(batch=args.batch, n_points=args.points, device=dev, k=args.k, rank=rank,
                         prefetch=not args.no_prefetch)
     stats_layout = amdist.PackedStats(13)
-    buckets = amdist.GradBuckets(int(args.grad_mb * 1e6 / 4), dev) if world > 1 and args.grad_mb > 0 else None
+    # N > 1: flat gradient buckets as DDP would reduce them; the step's packed statistics (loss terms, selected
+    # points per stage, per-class tp / union / count, computed inside the step) ride in the tail of the last bucket
+    buckets = (amdist.GradBuckets(int(args.grad_mb * 1e6 / 4), dev, tail_extra=stats_layout.size)
+               if world > 1 and args.grad_mb > 0 else None)
+    stats_sink = buckets.extra if buckets is not None else torch.zeros(stats_layout.size, device=dev)
+    replay.stats_sink = stats_sink
 
     use_graph = not args.no_graph
 
@@ -510,12 +515,10 @@ def run_ours(args):
             loss = replay.step()
         if world > 1:
             if buckets is not None:
-                buckets.launch(max(nb - 1, 0), nb)   # the last bucket is only ready when the backward ends
-            z = torch.zeros(13, device=dev)
-            buf = stats_layout.pack_device(loss, loss, loss, torch.zeros(4, device=dev), z, z, z)
-            amdist.all_reduce_packed(buf)
-            if buckets is not None:
+                buckets.launch(max(nb - 1, 0), nb)   # the last (1 MB) bucket + the packed statistics: ready when the backward ends
                 buckets.wait()
+            else:
+                amdist.all_reduce_packed(stats_sink)
         return loss
 
     def timed(n_steps, e2e, graph):
@@ -606,6 +609,7 @@ def run_ours(args):
     unpipelined = None
     if replay.prefetch:
         ru = PathReplay(batch=args.batch, n_points=args.points, device=dev, k=args.k, rank=rank, prefetch=False)
+        ru.stats_sink = stats_sink
         cur["replay"] = ru
         for _ in range(warm):
             one_step(False, False)
@@ -713,7 +717,9 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "batch": args.batch, "points_per_scene": args.points, "k": args.k,
                        "units_per_rank_per_step": 1, "parallelism": f"dp{world} (scene units, no data-path collective)",
                        "l2": "working set per step (6.45 GB of grouped tensors) exceeds the 126 MB L2; no flush needed",
-                       "grad_allreduce_mb": args.grad_mb if world > 1 else 0, "loss": last_loss},
+                       "grad_allreduce_mb": args.grad_mb if world > 1 else 0, "loss": last_loss,
+                       "reduced_stats": {k: (v.tolist() if hasattr(v, "tolist") else v)
+                                         for k, v in stats_layout.unpack(stats_sink.double().cpu()).items()}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": replay.h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps, "steps": args.steps,
                     "host_loop": "inputs copied from pinned host memory and the loss copied back every step; the host "

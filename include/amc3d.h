@@ -296,6 +296,13 @@ int amc3d_pointops_aggregation_backward(int n, int nsample, int c, int w_c, cons
 int amc3d_stage_labels(int m, int kr, int ncls, int has_ignore, long long ignore_index,
                        const long long *target, const int *nidx, int *cls, void *stream);
 
+/* Per-class confusion counts of a prediction against integer labels: out (3*ncls) f32 = [tp | #predicted |
+ * #labelled] (zeroed here), the quantities the trainer all-reduces every step (union = #predicted + #labelled - tp).
+ * pred NULL: the prediction is the label of the point's first listed neighbour, target[nbr[i*ld]].
+ * ref: utils/metrics.py ConfusionMatrix.update / tp / union / count; examples/segmentation/main_AA.py:461,496-507 */
+int amc3d_class_counts(int m, int ncls, const int *target, const int *pred, const int *nbr, int ld,
+                       float *out, void *stream);
+
 /* Neighbour lists below are given as (nbr, ld, ke): row i holds its ke neighbour indices at
  * nbr[i*ld .. i*ld+ke).  For a kNN result knn_idx (m,k) whose column 0 is the self match
  * (what the reference drops with [..., 1:], MarginContrast.py:226) pass nbr = knn_idx + 1,

@@ -30,12 +30,14 @@ def _worker(rank, world, port, out):
     buf = layout.pack(rank + 1.0, 0.5, 0.25, [len(units)] * 4, tp, tp * 2, tp * 3)
     amdist.all_reduce_packed(buf)
     stats = layout.unpack(buf)
-    buckets = amdist.GradBuckets(1000, "cpu", bucket_mb=0.001)
-    assert len(buckets.buckets) == 4
+    # 1000 gradient floats in 250-float buckets, a 100-float tail bucket that also carries the packed statistics
+    buckets = amdist.GradBuckets(1000, "cpu", bucket_mb=0.001, tail_mb=0.0004, tail_extra=layout.size)
+    assert [b.numel() for b in buckets.buckets] == [250, 250, 250, 150, 100 + layout.size]
+    assert buckets.extra.numel() == layout.size and buckets.extra.data_ptr() == buckets.flat[1000:].data_ptr()
     buckets.flat.fill_(rank + 1.0)
     buckets.launch()
     buckets.wait()
-    out[rank] = (units, stats["loss_sum"], stats["n_selected"], stats["tp"].tolist(), float(buckets.flat.sum()))
+    out[rank] = (units, stats["loss_sum"], stats["n_selected"], stats["tp"].tolist(), float(buckets.flat[:1000].sum()))
     dist.barrier()
     dist.destroy_process_group()
 

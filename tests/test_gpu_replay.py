@@ -117,3 +117,27 @@ def test_prefetch_pipeline_matches_unpipelined_batches():
          r.step_graph(*pin[1]).item()]         # -> loss of batch 1
     for got_i, want_i in zip(g, [ref[1], ref[2], ref[0], ref[1]]):
         assert abs(got_i - want_i) <= 1e-6 * abs(want_i), (g, ref)
+
+
+def test_step_statistics_match_torch_counts():
+    """the packed per-step statistics (selected points per stage, per-class tp / union / count of the stand-in
+    prediction) written inside the step == the same quantities from torch ops (main_AA.py:461,496-507 reduce them)"""
+    from amcontrast3d_b200.replay import PathReplay
+    from amcontrast3d_b200.dist import PackedStats
+    r = PathReplay(batch=2, n_points=4096, k=16, with_grouping=False)
+    layout = PackedStats(13)
+    r.stats_sink = torch.zeros(layout.size, device="cuda")
+    loss = r.step()
+    torch.cuda.synchronize()
+    st = layout.unpack(r.stats_sink.double().cpu())
+    geo = r._am_geometry
+    assert st["n_selected"] == [int(g["stats"][0]) for g in geo]
+    t = geo[0]["cls"].long()
+    pred = t[geo[0]["knn_idx"][:, 1].long()]
+    count = torch.bincount(t, minlength=13)
+    tp = torch.bincount(t[pred == t], minlength=13)
+    union = count + torch.bincount(pred, minlength=13) - tp
+    assert st["count"].tolist() == count.cpu().tolist() and int(count.sum()) == 2 * 4096
+    assert st["tp"].tolist() == tp.cpu().tolist()
+    assert st["union"].tolist() == union.cpu().tolist()
+    assert abs(st["loss_sum"] - loss.item()) <= 1e-6 * abs(loss.item())
