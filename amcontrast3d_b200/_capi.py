@@ -202,10 +202,20 @@ def ptr(t) -> int:
     return t.data_ptr()
 
 
-def stream(t) -> int:
-    import torch
+_raw_stream = None
 
-    return torch.cuda.current_stream(t.device).cuda_stream
+
+def stream(t) -> int:
+    """torch's current CUDA stream on the tensor's device, as the raw cudaStream_t value.  Through torch's C
+    accessor (one C call, ~0.2 us) rather than torch.cuda.current_stream(...).cuda_stream (a Python object per
+    call, ~4 us): with ~170 launches per step that alone is 0.7 ms of an eager step."""
+    global _raw_stream
+    if _raw_stream is None:
+        import torch
+
+        _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None) or (
+            lambda idx: torch.cuda.current_stream(idx).cuda_stream)
+    return _raw_stream(t.device.index)
 
 
 _NO_CPU = ("amc3d kernels need CUDA tensors: there is no CPU path in this package "
@@ -221,15 +231,21 @@ class _NoGuard:
 
 
 _NO_GUARD = _NoGuard()
+_cur_dev = None
 
 
 def guard(t):
     """Device guard for the launch; refuses CPU tensors loudly.  Switching devices is only needed
     when the tensor does not live on the current one (never, with one process per GPU)."""
-    import torch
-
     if not t.is_cuda:
         raise Amc3dError(_NO_CPU)
-    if t.device.index == torch.cuda.current_device():
+    global _cur_dev
+    if _cur_dev is None:
+        import torch
+
+        _cur_dev = getattr(torch._C, "_cuda_getDevice", None) or torch.cuda.current_device
+    if t.device.index == _cur_dev():
         return _NO_GUARD
+    import torch
+
     return torch.cuda.device(t.device)
