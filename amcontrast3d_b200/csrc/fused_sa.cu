@@ -194,7 +194,8 @@ fused_sa_fwd_kernel(const FusedFwdArgs a) {
              *acc_empty = bars + 2 * FS_MAX_STAGES + 2, *w_full = bars + 2 * FS_MAX_STAGES + 4;
 
     const int tid = threadIdx.x, warp = tid >> 5;
-    const long long Q = (long long)a.B * a.M;
+    const int Q = a.B * a.M;                               // queries (host checks B*M < 2^31)
+    const int nitems = (int)a.nitems, nsl = a.nslices;
 
     if (tid == 0) {
         for (int s = 0; s < FS_MAX_STAGES; ++s) {
@@ -224,22 +225,22 @@ fused_sa_fwd_kernel(const FusedFwdArgs a) {
         const int slot = tid & 7, rsub = tid >> 3;                 // 8 lanes per 128-byte row, FS_RPP rows per pass
         // neighbour index of the grouped positions this thread fetches in an item (raw loads: nothing may depend on
         // them until the item starts, so that they are in flight during the previous item's chunks)
-        auto load_meta = [&](long long item, int (&nidx)[FS_NPASS]) {
-            const long long q0 = (item / a.nslices) * QPT;
+        auto load_meta = [&](int item, int (&nidx)[FS_NPASS]) {
+            const int q0 = (item / nsl) * QPT;
 #pragma unroll
             for (int i = 0; i < FS_NPASS; ++i) {
                 const int r = i * FS_RPP + rsub;
-                const long long qg = q0 + r / NS;
-                nidx[i] = qg < Q ? __ldg(a.idx + qg * NS + (r % NS)) : 0;
+                const int qg = q0 + r / NS;
+                nidx[i] = qg < Q ? __ldg(a.idx + (long long)qg * NS + (r % NS)) : 0;
             }
         };
         // support row (b*N + n) per position, -1 past the end
-        auto rows_of = [&](long long item, const int (&nidx)[FS_NPASS], long long (&frow)[FS_NPASS]) {
-            const long long q0 = (item / a.nslices) * QPT;
+        auto rows_of = [&](int item, const int (&nidx)[FS_NPASS], long long (&frow)[FS_NPASS]) {
+            const int q0 = (item / nsl) * QPT;
 #pragma unroll
             for (int i = 0; i < FS_NPASS; ++i) {
-                const long long qg = q0 + (i * FS_RPP + rsub) / NS;
-                frow[i] = qg < Q ? (qg / a.M) * a.N + nidx[i] : -1;
+                const int qg = q0 + (i * FS_RPP + rsub) / NS;
+                frow[i] = qg < Q ? (long long)(qg / a.M) * a.N + nidx[i] : -1;
             }
         };
         auto fill_w = [&](unsigned char *wt, int o0, int kc, auto async_tag) {
@@ -259,9 +260,9 @@ fused_sa_fwd_kernel(const FusedFwdArgs a) {
                 }
             }
         };
-        auto fill_x = [&](unsigned char *xt, long long item, const long long (&frow)[FS_NPASS], int kc, auto async_tag) {
+        auto fill_x = [&](unsigned char *xt, int item, const long long (&frow)[FS_NPASS], int kc, auto async_tag) {
             constexpr bool ASYNC = decltype(async_tag)::value;
-            const long long q0 = (item / a.nslices) * QPT;
+            const long long q0 = (long long)(item / nsl) * QPT;
             const int k0 = kc * 32 + slot * 4;
 #pragma unroll
             for (int i = 0; i < FS_NPASS; ++i) {
@@ -288,10 +289,11 @@ fused_sa_fwd_kernel(const FusedFwdArgs a) {
         };
         using Async = std::integral_constant<bool, !X3>;           // TF32: cp.async ring; 3xTF32: through registers
         // hand chunk `c` (global chunk counter) to the MMA warp
-        auto publish = [&](long long c) {
+        auto publish_slot = [&](int slot_i) {
             if (a.fence_mode == 0) fence_async_smem();             // generic-proxy writes -> visible to the MMA (async proxy)
-            mbar_arrive(fs_smem(&full[c % S]));
+            mbar_arrive(fs_smem(&full[slot_i]));
         };
+        auto publish = [&](long long c) { publish_slot((int)(c % S)); };
         auto wait_groups = [&](int n) {                            // cp.async.wait_group needs an immediate
             switch (n) {
                 case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
@@ -314,34 +316,93 @@ fused_sa_fwd_kernel(const FusedFwdArgs a) {
         long long cur[FS_NPASS];
         int nxt[FS_NPASS];
         long long c = 0;                                           // chunks issued so far
-        if ((long long)blockIdx.x < a.nitems) load_meta(blockIdx.x, nxt);
-        for (long long item = blockIdx.x; item < a.nitems; item += gridDim.x) {
-            rows_of(item, nxt, cur);
-            if (item + gridDim.x < a.nitems) load_meta(item + gridDim.x, nxt);     // in flight during this item's chunks
-            const int o0 = (int)(item % a.nslices) * 128;
-            for (int kc = 0; kc < nchunks; ++kc, ++c) {
-                const int st = (int)(c % S);
-                if (c >= S) mbar_wait(fs_smem(&empty[st]), (uint32_t)((c / S - 1) & 1));
-                unsigned char *xt = ring + (size_t)st * slot_bytes;
-                fill_x(xt, item, cur, kc, Async{});
-                if (!wres) fill_w(xt + T_BYTES, o0, kc, Async{});
-                if (!X3 && a.fence_mode == 2) {
-                    // the barrier arrival fires when this thread's copies of the chunk have landed: nothing to wait for
-                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(fs_smem(&full[st])) : "memory");
-                } else if (!X3) {
-                    asm volatile("cp.async.commit_group;" ::: "memory");
-                    if (c >= S - 1) {                              // all but the newest S-1 groups have landed
-                        wait_groups(S - 1);
-                        publish(c - (S - 1));
+        if ((int)blockIdx.x < nitems) load_meta((int)blockIdx.x, nxt);
+        if (!X3) {
+            // TF32: the hot loop is one predicated 16-byte cp.async per row and chunk.  Everything that does not
+            // change per chunk is hoisted: swizzled destination offsets (per kernel), row pointers and the
+            // relative coordinates (per item; their loads are in flight while the feature chunks are issued).
+            uint32_t soff[FS_NPASS];
+#pragma unroll
+            for (int i = 0; i < FS_NPASS; ++i) soff[i] = sw128_off(i * FS_RPP + rsub, slot);
+            int st = 0, pass = 0;
+            const int kc_dp = a.C / 32;                            // chunk and slot that hold (dp, 0): C % 4 == 0
+            const bool dp_lane = slot == (a.C % 32) / 4;
+            for (int item = blockIdx.x; item < nitems; item += (int)gridDim.x) {
+                rows_of(item, nxt, cur);
+                if (item + (int)gridDim.x < nitems) load_meta(item + (int)gridDim.x, nxt); // in flight during this item's chunks
+                const int o0 = (item % nsl) * 128;
+                const float *xp[FS_NPASS], *wp[FS_NPASS];
+                float4 dp[FS_NPASS];
+#pragma unroll
+                for (int i = 0; i < FS_NPASS; ++i) {
+                    const bool live = cur[i] >= 0;
+                    xp[i] = live ? a.fT + cur[i] * a.C + slot * 4 : nullptr;
+                    const int o = o0 + i * FS_RPP + rsub;
+                    wp[i] = (!wres && o < a.O) ? a.Wp + (long long)o * a.Kp + slot * 4 : nullptr;
+                    dp[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (dp_lane && live) {
+                        const float *pp = a.xyz + cur[i] * 3;
+                        const float *qq = a.qxyz + ((long long)(item / nsl) * QPT + (i * FS_RPP + rsub) / NS) * 3;
+                        dp[i].x = (__ldg(pp) - __ldg(qq)) * a.inv_radius;
+                        dp[i].y = (__ldg(pp + 1) - __ldg(qq + 1)) * a.inv_radius;
+                        dp[i].z = (__ldg(pp + 2) - __ldg(qq + 2)) * a.inv_radius;
                     }
-                } else {
-                    publish(c);
+                }
+                for (int kc = 0; kc < nchunks; ++kc, ++c) {
+                    // ring position without divisions: chunk c sits in slot st on pass `pass` of the ring
+                    if (pass > 0) mbar_wait(fs_smem(&empty[st]), (uint32_t)((pass - 1) & 1));
+                    const uint32_t xs = fs_smem(ring + (size_t)st * slot_bytes);
+                    const int k0 = kc * 32 + slot * 4;
+                    const bool featk = k0 + 4 <= a.C, wk = k0 < a.Kp;
+                    if (kc == kc_dp && dp_lane) {                  // this lane's slot of this chunk is (dp, 0): plain stores
+#pragma unroll
+                        for (int i = 0; i < FS_NPASS; ++i) *reinterpret_cast<float4 *>(ring + (size_t)st * slot_bytes + soff[i]) = dp[i];
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < FS_NPASS; ++i) {
+                            const bool ok = featk && xp[i] != nullptr;
+                            cp_async16(xs + soff[i], ok ? xp[i] + kc * 32 : a.fT, ok);
+                        }
+                    }
+                    if (!wres) {
+#pragma unroll
+                        for (int i = 0; i < FS_NPASS; ++i) {
+                            const bool ok = wk && wp[i] != nullptr;
+                            cp_async16(xs + T_BYTES + soff[i], ok ? wp[i] + kc * 32 : a.Wp, ok);
+                        }
+                    }
+                    if (a.fence_mode == 2) {
+                        // the barrier arrival fires when this thread's copies of the chunk have landed: nothing to wait for
+                        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(fs_smem(&full[st])) : "memory");
+                    } else {
+                        asm volatile("cp.async.commit_group;" ::: "memory");
+                        if (c >= S - 1) {                          // all but the newest S-1 groups have landed:
+                            wait_groups(S - 1);                    // chunk c - (S-1), which sits in the NEXT slot
+                            publish_slot(st + 1 == S ? 0 : st + 1);
+                        }
+                    }
+                    if (++st == S) { st = 0; ++pass; }
                 }
             }
-        }
-        if (!X3 && a.fence_mode != 2) {                            // drain the ring
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            for (long long d = (c >= S - 1 ? c - (S - 1) : 0); d < c; ++d) publish(d);
+            if (a.fence_mode != 2) {                               // drain the ring
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                for (long long d = (c >= S - 1 ? c - (S - 1) : 0); d < c; ++d) publish_slot((int)(d % S));
+            }
+        } else {
+            int st = 0, pass = 0;
+            for (int item = blockIdx.x; item < nitems; item += (int)gridDim.x) {
+                rows_of(item, nxt, cur);
+                if (item + (int)gridDim.x < nitems) load_meta(item + (int)gridDim.x, nxt);
+                const int o0 = (item % nsl) * 128;
+                for (int kc = 0; kc < nchunks; ++kc, ++c) {
+                    if (pass > 0) mbar_wait(fs_smem(&empty[st]), (uint32_t)((pass - 1) & 1));
+                    unsigned char *xt = ring + (size_t)st * slot_bytes;
+                    fill_x(xt, item, cur, kc, Async{});
+                    if (!wres) fill_w(xt + T_BYTES, o0, kc, Async{});
+                    publish_slot(st);
+                    if (++st == S) { st = 0; ++pass; }
+                }
+            }
         }
     } else if (warp == FS_PW) {
         // ================================================================== MMA issuer (one elected lane)
@@ -350,15 +411,16 @@ fused_sa_fwd_kernel(const FusedFwdArgs a) {
             mbar_wait(fs_smem(w_full), 0);
             tc_fence_after();
         }
-        long long c = 0, it = 0;
-        for (long long item = blockIdx.x; item < a.nitems; item += gridDim.x, ++it) {
+        long long it = 0;
+        int st = 0;
+        uint32_t ph = 0;                                           // ring slot and its phase parity, kept incrementally
+        for (int item = blockIdx.x; item < nitems; item += (int)gridDim.x, ++it) {
             const int buf = (int)(it & 1);
             mbar_wait(fs_smem(&acc_empty[buf]), (uint32_t)(((it >> 1) & 1) ^ 1));   // the epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t d = tmem_base + (uint32_t)(buf * 128);
-            for (int kc = 0; kc < nchunks; ++kc, ++c) {
-                const int st = (int)(c % S);
-                mbar_wait(fs_smem(&full[st]), (uint32_t)((c / S) & 1));
+            for (int kc = 0; kc < nchunks; ++kc) {
+                mbar_wait(fs_smem(&full[st]), ph);
                 if (a.fence_mode != 0) fence_async_smem();
                 tc_fence_after();
                 if ((tid & 31) == 0) {
@@ -381,6 +443,7 @@ fused_sa_fwd_kernel(const FusedFwdArgs a) {
                     if (kc == nchunks - 1) umma_commit(fs_smem(&acc_full[buf]));
                 }
                 __syncwarp();
+                if (++st == S) { st = 0; ph ^= 1u; }
             }
         }
         tc_fence_before();
@@ -403,10 +466,10 @@ fused_sa_fwd_kernel(const FusedFwdArgs a) {
             csq = 0.f;
         };
         long long it = 0;
-        for (long long item = blockIdx.x; item < a.nitems; item += gridDim.x, ++it) {
+        for (int item = blockIdx.x; item < nitems; item += (int)gridDim.x, ++it) {
             const int buf = (int)(it & 1);
-            const long long q0 = (item / a.nslices) * QPT;
-            const int o = (int)(item % a.nslices) * 128 + lane_o;
+            const int q0 = (item / nsl) * QPT;
+            const int o = (item % nsl) * 128 + lane_o;
             if (o != co) { flush(); co = o; }
             const bool live = o < a.O;
             // gamma < 0: BatchNorm + ReLU decrease in y, the pooled maximum sits at the MINIMUM of y: track max of -y
@@ -439,7 +502,7 @@ fused_sa_fwd_kernel(const FusedFwdArgs a) {
                 const float best = (g2 ? m1 : m0) * sgn;
                 const int bi = g2 ? i1 : i0;
                 const long long qg = q0 + qi;
-                if (live && qg < Q) {
+                if (live && qg < (long long)Q) {
                     csum += s1a + s1b;
                     csq += s2a + s2b;
                     a.ysel[qg * a.O + o] = best;
@@ -543,7 +606,7 @@ extern "C" int amc3d_fused_sa_forward(int b, int n, int m, int c, int o, int nsa
     AMC3D_REQUIRE(c % 8 == 0, AMC3D_ELIMIT, "fused_sa_forward: C=%d is not a multiple of 8", c);
     AMC3D_REQUIRE(nsample == 16 || nsample == 32, AMC3D_ELIMIT, "fused_sa_forward: nsample=%d (16 and 32 are built)", nsample);
     AMC3D_REQUIRE(precision == 1 || precision == 3, AMC3D_EINVAL, "fused_sa_forward: precision=%d is not 1 (TF32) / 3 (3xTF32)", precision);
-    AMC3D_REQUIRE(b <= 65535, AMC3D_ELIMIT, "fused_sa_forward: batch %d > 65535", b);
+    AMC3D_REQUIRE(b <= 65535 && (long long)b * m < (1ll << 31) / 64, AMC3D_ELIMIT, "fused_sa_forward: batch %d x %d queries too large", b, m);
     if (b == 0 || m == 0) return 0;
     cudaStream_t st = as_stream(stream);
     FusedFwdArgs a;
