@@ -22,7 +22,7 @@ LIBNAME = "libamc3d_sm100a.so"
 LIBPATH = os.path.join(LIBDIR, LIBNAME)
 
 SOURCES = ["common.cu", "knn.cu", "knn_grid.cu", "batch_query.cu", "fps.cu", "group.cu", "amloss.cu", "refine.cu",
-           "pointops_packed.cu", "fused_sa.cu"]
+           "pointops_packed.cu", "fused_sa.cu", "voxel.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

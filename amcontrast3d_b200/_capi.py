@@ -60,6 +60,8 @@ SIGNATURES = {
                                _P, _P, _P],
     "amc3d_fused_sa_backward_scatter": [_I, _I, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "amc3d_fused_sa_moments": [_I, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P],
+    "amc3d_voxel_keys": [_LL, ctypes.c_double, _P, _P, _P, _P],
+    "amc3d_crop_dist2": [_LL, _P, _LL, _P, _P],
     "amc3d_three_nn": [_I, _I, _I, _P, _P, _P, _P, _P],
     "amc3d_three_interpolate": [_I, _I, _I, _I, _P, _P, _P, _P, _P],
     "amc3d_three_interpolate_grad": [_I, _I, _I, _I, _P, _P, _P, _P, _P],

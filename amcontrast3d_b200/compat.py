@@ -15,6 +15,11 @@ Three levels, matching the tiers of the drop-in boundary (INTEGR
                       get_subscene_label_CBL / RefinementMethod / posmask_searching and the two
                       criteria, i.e. the fused loss path.
 
+    install(tier=4)   additionally routes LocalAggregation.forward / SetAbstraction.forward of the reference's
+                      PointNeXt backbones (openpoints.models.backbone.pointnext_AA / pointnext_MM) through the
+                      fused grouping -> conv -> BatchNorm -> ReLU -> max operator (layers/fused.py); layers the
+                      operator does not cover keep the reference's composition.
+
 Call it once, before the reference's model / criterion modules are imported (tier 1) or right after
 (tiers 2-3 patch attributes of already-imported modules as well).  Nothing here touches files of the
 reference checkout.
@@ -97,4 +102,19 @@ def install(tier: int = 1, strict: bool = False):
         done += _rebind(_T2, strict)
     if tier >= 3:
         done += _rebind(_T3, strict)
+    if tier >= 4:
+        from .layers import fused
+        for name in ("openpoints.models.backbone.pointnext_AA", "openpoints.models.backbone.pointnext_MM",
+                     "openpoints.models.backbone.pointnext"):
+            try:
+                mod = sys.modules.get(name) or importlib.import_module(name)
+            except Exception:
+                if strict:
+                    raise
+                continue
+            for cls_name, which in (("LocalAggregation", "la"), ("SetAbstraction", "sa")):
+                cls = getattr(mod, cls_name, None)
+                if cls is not None:
+                    fused.bind(cls, which)
+                    done.append(f"{name}.{cls_name}.forward")
     return done

@@ -152,13 +152,13 @@ def _fusable(module, f):
 
 
 def local_aggregation_forward(module, pf, precision=None):
-    """LocalAggregation.forward(pf) (pointnext_AA.py:57-63) through the fused operator; falls back to the module's
-    own composition for configurations the operator does not cover (several conv layers, other feature types or
-    reductions, eval mode)."""
+    """LocalAggregation.forward(pf) (pointnext_AA.py:57-63) through the fused operator.  Returns None for
+    configurations the operator does not cover (several conv layers, other feature types or reductions, eval
+    mode, channel counts off the 8-grid): the caller runs the module's own composition."""
     p, f = pf
     cb = _fusable(module, f) if getattr(module, "reduction", "max") == "max" else None
     if cb is None:
-        return type(module).forward(module, pf) if type(module).forward is not local_aggregation_forward else None
+        return None
     conv, bn = cb
     g = module.grouper
     idx = ball_query(g.radius, g.nsample, p, p)
@@ -167,7 +167,7 @@ def local_aggregation_forward(module, pf, precision=None):
 
 def set_abstraction_forward(module, pf, precision=None):
     """SetAbstraction.forward(pf) (pointnext_AA.py:139-170) for the non-head, non-residual, strided layer:
-    FPS -> gather queries -> fused operator.  -> (new_p, f)"""
+    FPS -> gather queries -> fused operator.  -> (new_p, f), or None when not covered."""
     p, f = pf
     if module.is_head or module.all_aggr or module.use_res:
         return None
@@ -180,3 +180,22 @@ def set_abstraction_forward(module, pf, precision=None):
     g = module.grouper
     idx = ball_query(g.radius, g.nsample, p, new_p.contiguous())
     return new_p, fused_group_conv_bn_relu_max(new_p, p, f, idx, conv.weight, bn, g.radius, g.normalize_dp, precision)
+
+
+def bind(cls, which: str):
+    """Route `cls.forward` (the reference's LocalAggregation / SetAbstraction class, or a subclass) through the fused
+    operator, keeping the original forward for everything the operator does not cover.  Idempotent."""
+    if getattr(cls, "_amc3d_fused", False):
+        return cls
+    orig = cls.forward
+    fn = local_aggregation_forward if which == "la" else set_abstraction_forward
+
+    def forward(self, pf):
+        out = fn(self, pf)
+        return orig(self, pf) if out is None else out
+
+    forward.__doc__ = orig.__doc__
+    cls._amc3d_orig_forward = orig
+    cls.forward = forward
+    cls._amc3d_fused = True
+    return cls

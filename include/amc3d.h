@@ -201,6 +201,19 @@ int amc3d_fused_sa_moments(int b, int n, int m, int nsample, float radius, int n
                            float *dpsum, double *mom, void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Input side: voxel hash and crop distances of the dataset code
+ * ------------------------------------------------------------------------------------- */
+
+/* keys[i] = FNV64-1A of floor(coord[i] / voxel_size) (FP64 division and floor, as numpy evaluates it);
+ * cells (n,3) i64 receives the integer cell coordinates if not NULL (the 'ravel' hash is formed from them).
+ * ref: openpoints/dataset/data_util.py:92-105 fnv_hash_vec, :125-131 voxelize */
+int amc3d_voxel_keys(long long n, double voxel_size, const float *coord, unsigned long long *keys,
+                     long long *cells, void *stream);
+/* out[i] = sum((coord[i] - coord[init_idx])^2), FP32, the sort key of crop_pc.
+ * ref: openpoints/dataset/data_util.py:158-160 crop_pc */
+int amc3d_crop_dist2(long long n, const float *coord, long long init_idx, float *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * pointops family: packed (n,3) xyz / (n,c) features with cumulative i32 `offset` ends
  * ------------------------------------------------------------------------------------- */
 

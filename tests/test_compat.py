@@ -53,3 +53,42 @@ def test_reference_wrappers_bind_to_the_library():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_install_tier4_routes_module_forwards_through_the_fused_operator():
+    """tier 4 wraps LocalAggregation.forward / SetAbstraction.forward of the backbone modules; configurations the
+    operator does not cover (here: CPU tensors) fall through to the original forward"""
+    import types
+    import torch
+    from amcontrast3d_b200 import compat
+    name = "openpoints.models.backbone.pointnext_AA"
+    saved = {k: sys.modules.get(k) for k in ("pointnet2_batch_cuda", "pointops_cuda", name)}
+
+    class LocalAggregation(torch.nn.Module):
+        def forward(self, pf):
+            return "reference composition"
+
+    class SetAbstraction(LocalAggregation):
+        pass
+
+    fake = types.ModuleType(name)
+    fake.LocalAggregation, fake.SetAbstraction = LocalAggregation, SetAbstraction
+    try:
+        sys.modules[name] = fake
+        done = compat.install(tier=4)
+        assert f"{name}.LocalAggregation.forward" in done and f"{name}.SetAbstraction.forward" in done
+        assert LocalAggregation._amc3d_fused and SetAbstraction._amc3d_fused
+        m = LocalAggregation()
+        m.grouper = types.SimpleNamespace(radius=0.1, nsample=32, normalize_dp=True)
+        m.feature_type, m.reduction = "dp_fj", "max"
+        m.convs = torch.nn.Sequential(torch.nn.Sequential(torch.nn.Conv2d(35, 32, 1, bias=False), torch.nn.BatchNorm2d(32),
+                                                          torch.nn.ReLU()))
+        assert m((torch.zeros(1, 8, 3), torch.zeros(1, 32, 8))) == "reference composition"     # CPU tensors: not fusable
+        compat.install(tier=4)                                                                # idempotent
+        assert LocalAggregation.forward is not LocalAggregation._amc3d_orig_forward
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v

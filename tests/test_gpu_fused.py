@@ -161,3 +161,43 @@ def test_unsupported_configurations_use_the_module_composition():
     f = torch.randn(1, 32, 64, device="cuda")
     assert fused._fusable(mod, f) is None
     assert not fused.supported(30, 32) and not fused.supported(32, 24) and fused.supported(64, 32)
+
+
+def test_bound_reference_module_runs_the_fused_operator():
+    """what compat.install(tier=4) does to the reference's classes (layers/fused.bind), on a subclass so that the
+    other tests of this process keep the unbound reference: the module call a PointNeXt backbone makes runs the
+    fused operator, and a configuration it does not cover falls back to the reference's composition"""
+    from oracle import ref_python as rp
+    if not rp.available():
+        pytest.skip("reference Python not available")
+    rp.import_reference(1)
+    from amcontrast3d_b200.layers import fused
+    from make_fused_golden import CASES, fused_inputs
+    g = np.load(PATH)
+    name = "la_c64_ns32"
+    kind, B, N, cin, cout, stride, radius, nsample = CASES[name]
+    inp = fused_inputs(name)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False                 # -> the FP32-faithful mode is the default precision
+    try:
+        ref_mod = _module(kind, cin, cout, stride, radius, nsample)
+        Bound = fused.bind(type("BoundLocalAggregation", (type(ref_mod),), {}), "la")
+        assert Bound._amc3d_fused and not getattr(type(ref_mod), "_amc3d_fused", False)
+        ref_mod.__class__ = Bound
+        mod = ref_mod.cuda()
+        conv, bn = mod.convs[0][0], mod.convs[0][1]
+        with torch.no_grad():
+            conv.weight.copy_(torch.from_numpy(inp["w"]).view(cout, cin + 3, 1, 1))
+            bn.weight.copy_(torch.from_numpy(inp["gamma"]))
+            bn.bias.copy_(torch.from_numpy(inp["beta"]))
+        mod.train()
+        p = torch.from_numpy(inp["xyz"]).cuda()
+        f = torch.from_numpy(inp["f"]).cuda()
+        y = mod((p, f))
+        assert rel_err(y.detach().cpu().numpy(), g[f"{name}/y"]) < TOL
+        assert int(bn.num_batches_tracked) == 1             # the fused path updated the running statistics
+        mod.eval()                                          # not covered: the reference's own composition answers
+        y_eval = mod((p, f))
+        assert y_eval.shape == y.shape and torch.isfinite(y_eval).all()
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
