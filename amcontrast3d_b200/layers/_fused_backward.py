@@ -67,14 +67,14 @@ def backward(ctx, grad_out):
         Sx = torch.cat([Fw.sum(0), mom[0:3].float()])
         c1W = c1[:, None] * W
         Qm = W.t() @ c1W                                     # W'^T diag(c1) W'      (Kq, Kq)
-        v = W.t() @ c0
+        v = (W.t() @ c0[:, None]).t()                        # (1, Kq)
         dWp = torch.cat([A.t() @ f2, wdp.float()], 1)        # the arg-max term
-        dWp -= c0[:, None] * Sx[None, :]
-        dWp -= c1W @ Sxx
+        dWp.addmm_(c0[:, None], Sx[None, :], alpha=-1.0)
+        dWp.addmm_(c1W, Sxx, alpha=-1.0)
         dfT = A @ W[:, :C]                                   # the arg-max term       (B*N, C)
-        dfT -= cnt * v[None, :C]
-        dfT -= Fw @ Qm[:C, :C].t()
-        dfT -= dps @ Qm[:C, C:].t()
+        dfT.addmm_(cnt, v[:, :C], alpha=-1.0)
+        dfT.addmm_(Fw, Qm[:C, :C].t(), alpha=-1.0)
+        dfT.addmm_(dps, Qm[:C, C:].t(), alpha=-1.0)
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
     dW = torch.cat([dWp[:, C:], dWp[:, :C]], 1).reshape(wshape)

@@ -445,18 +445,54 @@ def time_fused_operator(replay, dev, iters=3):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / iters
 
+    def timed_graph(fn):
+        """the same forward + backward pass recorded into ONE CUDA graph and replayed: what the pass costs once
+        per-call Python and launch latency are out of the picture (None if the pass cannot be captured)"""
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    fn(True)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize()
+            for w in work:
+                w[5].grad = None
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_):
+                fn(True)
+            for _ in range(2):
+                g_.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                g_.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            del g_
+            return round(ms, 3)
+        except Exception as e:
+            torch.cuda.synchronize()
+            return f"not captured: {type(e).__name__}: {e}"[:160]
+
     res = {}
     try:
         f_fwd, f_all = timed(fused_pass, False), timed(fused_pass, True)
         c_fwd, c_all = timed(composed_pass, False), timed(composed_pass, True)
+        f_graph = timed_graph(fused_pass)
+        c_graph = timed_graph(composed_pass)
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
         tf32_peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
         res = {"layers": len(work), "conv_gflop_fwd": round(flop / 1e9, 1),
-               "fused": {"fwd_ms": round(f_fwd, 3), "fwd_bwd_ms": round(f_all, 3)},
-               "composition": {"fwd_ms": round(c_fwd, 3), "fwd_bwd_ms": round(c_all, 3),
+               "fused": {"fwd_ms": round(f_fwd, 3), "fwd_bwd_ms": round(f_all, 3), "fwd_bwd_graph_ms": f_graph},
+               "composition": {"fwd_ms": round(c_fwd, 3), "fwd_bwd_ms": round(c_all, 3), "fwd_bwd_graph_ms": c_graph,
                                "what": "QueryAndGroup (this package's grouping kernels) + cat + cuDNN Conv2d 1x1 (TF32) + "
                                        "BatchNorm2d (training) + ReLU + max, torch autograd"},
                "speedup_fwd": round(c_fwd / f_fwd, 2), "speedup_fwd_bwd": round(c_all / f_all, 2),
+               "speedup_fwd_bwd_graph": (round(c_graph / f_graph, 2) if isinstance(f_graph, float) and isinstance(c_graph, float)
+                                         else None),
                "fused_fwd_tflops": round(flop / (f_fwd * 1e-3) / 1e12, 1),
                "tensor_roofline": {"bound": "tensor", "achieved": round(flop / (f_fwd * 1e-3) / 1e12, 1), "peak": tf32_peak,
                                    "unit": "TFLOP/s", "frac": round(flop / (f_fwd * 1e-3) / 1e12 / tf32_peak, 4),
@@ -681,12 +717,17 @@ def run_ours(args):
         dom = max(hbm_rows, key=lambda r: r["ms"])
         per_launch_ms = dom["ms"] / dom["calls"]
         t = (traffic or {}).get(dom["entry"])
+        t_alg = ((traffic or {}).get("algorithmic") or {}).get(dom["entry"])
         roofline = {"kernel": f"{KERNEL_OF[dom['entry']]} via {dom['entry']}", "bound": "hbm", "achieved": dom["gbs"],
                     "peak": hbm_peak, "unit": "GB/s", "frac": dom["frac_hbm_peak"], "peak_source": peak_src,
                     "share_of_step": dom["share"], "launches_per_step": dom["calls"],
                     "ms_per_launch": round(per_launch_ms, 4),
                     "algorithmic_bytes_per_launch": round(agg[dom["entry"]]["byte"] / dom["calls"]),
                     "traffic": t,
+                    "traffic_note": (f"ncu dram__bytes_read+write of one launch at the largest feature-grouping shape "
+                                     f"{(traffic or {}).get('shape')} ({t_alg:.4g} algorithmic bytes there: ratio "
+                                     f"{t / t_alg:.3f}); profiles/ncu_traffic.json, profiles/r02_kernels_ncu.md"
+                                     if t and t_alg else None),
                     "note": "measured on a single-stream pass of the step; per-launch figures are means over the step's "
                             "launches of this entry point (transpose / "
                             "memset / accumulate launches of the call included in the time); FPS, the largest single "

@@ -1,12 +1,12 @@
-"""A lean program for the per-kernel ncu captures of profiles/ (ncu saves and restores the memory a profiled kernel
-writes on each of its ~40 passes, so the captured process must not hold the 6 GB of grouped tensors a whole step
-produces):  the config-2 geometry + loss path WITHOUT the grouping tensors (FPS chain, self / label kNN, three_nn,
-loss forward), one ball query per level, and ONE grouping gather + scatter-add and one three_interpolate pair at
-their largest config-2 shape.
+"""ONE launch of each kernel the per-kernel ncu summaries of profiles/ are taken on, at its BASELINE config-2 shape
+(ncu replays a profiled kernel ~40 times and saves / restores the memory it writes on every pass, so the captured
+process holds nothing it does not need):
 
     python tools/ncu_targets.py > plain.log && ncu --set full --clock-control none \
-        -k regex:'knn_wq_kernel|knn_tq_kernel|ball_wq_kernel|amloss_forward_kernel|fps_cluster_kernel|group_fwd_tma_kernel|group_bwd_tma_kernel|interp_fwd_tma|interp_bwd_tma' \
-        -s <launches of pass 1> -o gpurun_out/r02_kernels python tools/ncu_targets.py
+        -k regex:'knn_wq_kernel|knn_tq_kernel|ball_wq_kernel|amloss_forward_kernel|fps_cluster_kernel|group_fwd_tma_kernel|group_bwd_tma_kernel|fused_sa_fwd_kernel' \
+        -o /tmp/r02_kernels python tools/ncu_targets.py
+    ncu -i /tmp/r02_kernels.ncu-rep --page raw --csv > gpurun_out/r02_kernels_raw.csv      # small; summarised by
+    python tools/ncu_kernel_table.py gpurun_out/r02_kernels_raw.csv > profiles/r02_kernels_ncu.md
 """
 import os
 import sys
@@ -15,25 +15,33 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-from amcontrast3d_b200.layers import ball_query, grouping_operation, three_interpolation  # noqa: E402
-from amcontrast3d_b200.replay import PathReplay  # noqa: E402
+from amcontrast3d_b200 import _amloss, scenes  # noqa: E402
+from amcontrast3d_b200.layers import ball_query, furthest_point_sample, grouping_operation, three_nn  # noqa: E402
+from amcontrast3d_b200.layers.fused import FusedGroupConvBNReLUMax  # noqa: E402
+from amcontrast3d_b200.replay import aa_args  # noqa: E402
 
-passes = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-r = PathReplay(batch=8, n_points=24000, k=16, with_grouping=False, geometry_stream=False, prefetch=False)
-p = r._fps_chain(r.d_xyz)
+xyz, lab = scenes.batch_of_scenes(8, 24000, "surface")
+p0 = torch.from_numpy(xyz).cuda()
+labels = torch.from_numpy(lab).cuda().reshape(-1)
+idx = furthest_point_sample(p0, 6000)                                                  # fps_cluster_kernel<16,12,4>
+p1 = torch.gather(p0, 1, idx.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+flat = p0.reshape(-1, 3).contiguous()
+o = torch.tensor([flat.shape[0]], dtype=torch.int32, device="cuda")
+knn_idx, _, order = _amloss.knn_raw(16, flat, flat, o, o, want_order=True)              # knn_wq_kernel<1>: 192 000 self queries
+three_nn(p0, p1)                                                                       # knn_tq_kernel<3>
+bq = ball_query(0.2, 32, p1, p1)                                                       # ball_wq_kernel<1>
+cls, _ = _amloss.stage_labels(labels, 13, None)
+nl = _amloss.NeighbourList(knn_idx, drop_self=True)
+posbits, cnt, mx = _amloss.posmask_count(nl, cls)
+a, stats = _amloss.ambiguity(flat, nl, posbits, cnt, mx, "Method2", 0.04, 0.5)
+f0 = torch.randn(flat.shape[0], 64, device="cuda", requires_grad=True)
+loss = _amloss.am_loss(f0, nl, posbits, a, stats, aa_args(16), _amloss.compact_order(order, a))   # amloss_forward_kernel<16,1>
 f = torch.randn(8, 128, 6000, device="cuda", requires_grad=True)
-fc = torch.randn(8, 128, 6000, device="cuda", requires_grad=True)
-for _ in range(passes):
-    loss = r.step()                                            # 4 FPS, 7 kNN, 4 three_nn + interpolate, loss
-    for l in range(1, 5):                                      # the two ball-query shapes of every level
-        ball_query(0.1 * 2 ** (l - 1), 32, p[l - 1], p[l])
-        idx = ball_query(0.1 * 2 ** l, 32, p[l], p[l])
-        if l == 1:
-            idx1 = idx
-    out = grouping_operation(f, idx1)                          # (8,128,6000) x (6000,32): the largest feature grouping
-    out.backward(torch.ones_like(out))
-    up = three_interpolation(p[0], p[1], fc)                   # 24000 <- 6000, C = 128
-    up.backward(torch.ones_like(up))
-    del out, up
+out = grouping_operation(f, bq)                                                        # group_fwd_tma_kernel<4>
+out.backward(torch.ones_like(out))                                                     # group_bwd_tma_kernel<1>
+del out
+w = torch.randn(128, 131, device="cuda") / 11.4
+y, _, _ = FusedGroupConvBNReLUMax.apply(f.detach(), w, torch.ones(128, device="cuda"), torch.zeros(128, device="cuda"),
+                                        p1, p1, bq, 0.2, True, 1e-5, "tf32")            # fused_sa_fwd_kernel<32,false>
 torch.cuda.synchronize()
-print("loss", float(loss))
+print("loss", float(loss), "fused mean", float(y.mean()))
