@@ -44,7 +44,8 @@ class PathReplay:
 
     def __init__(self, batch=8, n_points=24000, device="cuda", k=16, num_classes=13, ignore_index=None,
                  kind="surface", rank=0, first_scene=0, arch=XL, refine=False, refine_k=12, seed=0,
-                 with_grouping=True, with_loss=True, geometry_stream=True, prefetch=False, loss_args=None):
+                 with_grouping=True, with_loss=True, geometry_stream=True, prefetch=False, loss_args=None,
+                 fused_conv=False):
         self.B, self.N, self.device = batch, n_points, torch.device(device)
         self.num_classes, self.ignore_index = num_classes, ignore_index
         self.args = aa_args(k, **(loss_args or {}))      # e.g. ScanNet / MM: temperature=0.5, nu=0.6
@@ -94,6 +95,19 @@ class PathReplay:
         self.sa = [None] + [QueryAndGroup(r * 2 ** (l - 1), arch["nsample"], normalize_dp=True) for l in range(1, nlev)]
         self.la = [None] + [QueryAndGroup(r * 2 ** l, arch["nsample"], normalize_dp=True) for l in range(1, nlev)]
         self.head = ContrastHead()
+        # fused_conv: every grouping of the encoder is replaced by the fused grouping -> 1x1 conv -> BatchNorm -> ReLU ->
+        # max operator (layers/fused.py) with that layer's conv / BatchNorm parameters — what a PointNeXt step executes
+        # when compat tier 4 is installed.  The (B, 3+C, M, 32) grouped tensors then never exist; the step now contains
+        # the 19 convolutions (865 GFLOP forward at config 2), which the plain replay leaves to the model.
+        self.fused_conv = fused_conv
+        if fused_conv:
+            import torch.nn as nn
+            self.fparams = {}
+            for l in range(1, nlev):
+                for i in range(arch["blocks"][l]):                      # i = 0: SetAbstraction, i >= 1: LocalAggregation
+                    cin = self.C[l - 1] if i == 0 else self.C[l]
+                    w = (torch.randn((self.C[l], cin + 3), device=self.device, generator=g) / (cin + 3) ** 0.5).requires_grad_(True)
+                    self.fparams[(l, i)] = (w, nn.BatchNorm2d(self.C[l]).to(self.device))
         # synthetic upstream gradients: one buffer, viewed per output
         self._gbuf = None
         self.points_per_step = batch * n_points
@@ -108,6 +122,23 @@ class PathReplay:
     def zero_grads(self):
         for t in self.F + self.f_dec:
             t.grad = None
+        if self.fused_conv:
+            for w, bn in self.fparams.values():
+                w.grad = None
+                bn.weight.grad = None
+                bn.bias.grad = None
+
+    def _aggregate(self, l, i, grouper, q, s, feats, idx=None):
+        """One neighbourhood aggregation of the encoder: the grouped features (what the reference's modules feed their
+        convolution), or — fused_conv — the output of the fused grouping + conv + BatchNorm + ReLU + max operator."""
+        if not self.fused_conv:
+            return grouper(q, s, feats, idx=idx)[1]
+        from .layers import ball_query
+        from .layers.fused import fused_group_conv_bn_relu_max
+        if idx is None:
+            idx = ball_query(grouper.radius, grouper.nsample, s, q)
+        w, bn = self.fparams[(l, i)]
+        return fused_group_conv_bn_relu_max(q, s, feats, idx, w, bn, grouper.radius, True, "tf32")
 
     def forward(self, xyz=None, labels=None):
         """-> (loss, outputs needing a synthetic upstream gradient)"""
@@ -168,11 +199,9 @@ class PathReplay:
             for l in range(1, nlev):
                 main.wait_event(ev_lvl[l])
                 if self.with_grouping:
-                    dp, fj = self.sa[l](p[l], p[l - 1], self.F[l - 1], idx=bq_sa[l])
-                    outs.append(fj)
+                    outs.append(self._aggregate(l, 0, self.sa[l], p[l], p[l - 1], self.F[l - 1], bq_sa[l]))
                     for i in range(arch["blocks"][l] - 1):
-                        dp, fj = self.la[l](p[l], p[l], self.F[l], idx=bq_la[l][i])
-                        outs.append(fj)
+                        outs.append(self._aggregate(l, i + 1, self.la[l], p[l], p[l], self.F[l], bq_la[l][i]))
             for l in range(nlev - 1, 0, -1):
                 main.wait_event(ev_up[l])
                 outs.append(three_interpolation(p[l - 1], p[l], self.F[l], nn=nn3[l]))
@@ -185,11 +214,9 @@ class PathReplay:
                 idx = furthest_point_sample(p[l - 1], self.n[l]).long()
                 p.append(torch.gather(p[l - 1], 1, idx.unsqueeze(-1).expand(-1, -1, 3)).contiguous())
                 if self.with_grouping:
-                    dp, fj = self.sa[l](p[l], p[l - 1], self.F[l - 1])
-                    outs.append(fj)
-                    for _ in range(arch["blocks"][l] - 1):
-                        dp, fj = self.la[l](p[l], p[l], self.F[l])
-                        outs.append(fj)
+                    outs.append(self._aggregate(l, 0, self.sa[l], p[l], p[l - 1], self.F[l - 1]))
+                    for i in range(arch["blocks"][l] - 1):
+                        outs.append(self._aggregate(l, i + 1, self.la[l], p[l], p[l], self.F[l]))
             for l in range(nlev - 1, 0, -1):
                 outs.append(three_interpolation(p[l - 1], p[l], self.F[l]))
         return self._loss_tail(p, labels), outs
@@ -317,11 +344,9 @@ class PathReplay:
         outs = []
         for l in range(1, nlev):
             if self.with_grouping:
-                dp, fj = self.sa[l](p[l], p[l - 1], self.F[l - 1], idx=G["sa"][l])
-                outs.append(fj)
+                outs.append(self._aggregate(l, 0, self.sa[l], p[l], p[l - 1], self.F[l - 1], G["sa"][l]))
                 for i in range(arch["blocks"][l] - 1):
-                    dp, fj = self.la[l](p[l], p[l], self.F[l], idx=G["la"][l][i])
-                    outs.append(fj)
+                    outs.append(self._aggregate(l, i + 1, self.la[l], p[l], p[l], self.F[l], G["la"][l][i]))
         for l in range(nlev - 1, 0, -1):
             outs.append(three_interpolation(p[l - 1], p[l], self.F[l], nn=G["nn3"][l]))
         self._am_geometry = G["am"]

@@ -661,6 +661,36 @@ def run_ours(args):
         del ru
         torch.cuda.empty_cache()
 
+    # the same unit with every grouping of the encoder replaced by the fused grouping + conv + BN + ReLU + max operator
+    # (compat tier 4): no grouped tensor exists in this step; it additionally executes the 19 convolutions
+    fused_step = None
+    if world == 1 and not args.no_fused:
+        try:
+            rf = PathReplay(batch=args.batch, n_points=args.points, device=dev, k=args.k, rank=rank, prefetch=not args.no_prefetch,
+                            fused_conv=True)
+            cur["replay"] = rf
+            for _ in range(warm):
+                one_step(False, False)
+            if use_graph:
+                rf.capture(warmup=1)
+                for _ in range(warm):
+                    one_step(False, True)
+            ms_f, _ = timed(args.steps, False, use_graph)
+            fused_step = {"ms_per_step": ms_f / args.steps, "value": args.batch * args.points / (ms_f / args.steps / 1e3),
+                          "gpu_launches": int(getattr(rf, "graph_launches", 0)),
+                          "what": "path replay with the 19 groupings replaced by the fused grouping -> 1x1 conv -> BatchNorm -> "
+                                  "ReLU -> max operator (TF32), forward + backward: the 6.45 GB of grouped tensors are gone "
+                                  "from the step, which now also contains the 19 convolutions (865 GFLOP forward) that the "
+                                  "headline step leaves to the model"}
+        except Exception as e:
+            fused_step = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+        cur["replay"] = replay
+        try:
+            del rf
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+
     ms_step = ms_total / args.steps
     pts = args.batch * args.points
     value = world * pts / (ms_step / 1e3)
@@ -779,7 +809,7 @@ def run_ours(args):
                             "against it — the rest of their issue slots is box tests and top-k maintenance, see "
                             "profiles/r02_search_ncu.md for issue-slot utilisation"},
             "kernels": kernels, "kernel_ms_per_step": round(total_ms, 3), "cpu_baseline": cpu_baseline,
-            "ref_gpu": ref_gpu, "fused_operator": fused}
+            "ref_gpu": ref_gpu, "fused_operator": fused, "fused_step": fused_step}
     print(json.dumps(line), flush=True)
     if world > 1:
         tdist.destroy_process_group()
