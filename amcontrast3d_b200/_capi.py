@@ -57,7 +57,7 @@ SIGNATURES = {
     "amc3d_gather_points_grad": [_I, _I, _I, _I, _P, _P, _P, _P],
     "amc3d_transpose_batched": [_I, _I, _I, _P, _P, _P],
     "amc3d_fused_sa_forward": [_I, _I, _I, _I, _I, _I, _F, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
-                               _P, _P, _P],
+                               _P, _P, _P, _P],
     "amc3d_fused_sa_backward_scatter": [_I, _I, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "amc3d_fused_sa_moments": [_I, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P],
     "amc3d_voxel_keys": [_LL, ctypes.c_double, _P, _P, _P, _P],
@@ -161,7 +161,7 @@ def _kernels_in(name: str, args) -> int:
     if name in ("amc3d_three_interpolate_grad_ws", "amc3d_three_interpolate_grad_ws_set"):
         return 2 if args[-2] else 1            # scatter + transpose-accumulate (plus a memset)
     if name == "amc3d_fused_sa_forward":
-        return 3                               # GEMM + statistics + normalise
+        return 4                               # weight tiles + GEMM + statistics + normalise
     if name in ("amc3d_refine_backward", "amc3d_ambiguity", "amc3d_ambiguity_backend"):
         return 2                               # (boundary count + ambiguity)
     return 1

@@ -149,12 +149,30 @@ __device__ __forceinline__ void tmem_ld_query<16>(uint32_t taddr, float (&v)[16]
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// W' (O, Kp) -> operand tiles: block (slice j, chunk kc) holds rows j*128 .. j*128+127, columns kc*32 .. kc*32+31 with the
+// 16-byte slot c of row r at r*128 + ((c ^ (r & 7)) << 4), zeros outside the matrix; X3 adds the lo = x - rna(x) tile.
+template <bool X3>
+__global__ void __launch_bounds__(256)
+fused_sa_wprep_kernel(int O, int Kp, int nchunks, const float *__restrict__ Wp, float *__restrict__ Wsw) {
+    const int blk = blockIdx.x, j = blk / nchunks, kc = blk % nchunks;
+    unsigned char *dst = reinterpret_cast<unsigned char *>(Wsw) + (size_t)blk * (X3 ? 2 : 1) * FS_NT * FS_ROWB;
+    for (int e = threadIdx.x; e < FS_NT * 8; e += 256) {
+        const int r = e >> 3, c = e & 7;
+        const int o = j * 128 + r, k0 = kc * 32 + c * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (o < O && k0 < Kp) v = __ldg(reinterpret_cast<const float4 *>(Wp + (long long)o * Kp + k0));
+        fs_store<X3>(dst, dst + FS_NT * FS_ROWB, sw128_off(r, c), v);
+    }
+}
+
 struct FusedFwdArgs {
     const float *fT;        // (B, N, C) channel-contiguous features
     const float *xyz;       // (B, N, 3) support points
     const float *qxyz;      // (B, M, 3) query points
     const int *idx;         // (B, M, NS)
     const float *Wp;        // (O, Kp): [W[:, 3:3+C] | W[:, 0:3] | 0]
+    const float *Wsw;       // the same weights as ready-made operand tiles: block (slice, chunk) = 128 rows x 128 B in the
+                            // swizzled layout the MMA reads ([hi | lo] halves for 3xTF32), so a chunk is ONE bulk copy
     const float *gamma;     // (O) BatchNorm weight: its sign selects max or min
     float *ysel;            // (B*M, O) pre-normalisation extreme of y over the neighbourhood
     unsigned char *arg;     // (B*M, O) sample index of that extreme (first one)
@@ -206,7 +224,7 @@ fused_sa_fwd_kernel(const FusedFwdArgs a) {
             mbar_init(fs_smem(&acc_full[b]), 1);                   // one tcgen05.commit
             mbar_init(fs_smem(&acc_empty[b]), FS_EPI);             // every epilogue thread arrives
         }
-        mbar_init(fs_smem(w_full), FS_PROD);
+        mbar_init(fs_smem(w_full), 1);                             // one arrive.expect_tx; the bulk copies complete it
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == FS_PW) {                                           // TMEM: two accumulators of 128 lanes x 128 columns
@@ -241,23 +259,6 @@ fused_sa_fwd_kernel(const FusedFwdArgs a) {
             for (int i = 0; i < FS_NPASS; ++i) {
                 const int qg = q0 + (i * FS_RPP + rsub) / NS;
                 frow[i] = qg < Q ? (long long)(qg / a.M) * a.N + nidx[i] : -1;
-            }
-        };
-        auto fill_w = [&](unsigned char *wt, int o0, int kc, auto async_tag) {
-            constexpr bool ASYNC = decltype(async_tag)::value;
-            const int k0 = kc * 32 + slot * 4;
-#pragma unroll
-            for (int i = 0; i < FS_NPASS; ++i) {
-                const int r = i * FS_RPP + rsub;
-                const int o = o0 + r;
-                const bool ok = o < a.O && k0 < a.Kp;
-                if (ASYNC) {
-                    cp_async16(fs_smem(wt) + sw128_off(r, slot), ok ? a.Wp + (long long)o * a.Kp + k0 : a.Wp, ok);
-                } else {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ok) v = __ldg(reinterpret_cast<const float4 *>(a.Wp + (long long)o * a.Kp + k0));
-                    fs_store<X3>(wt, wt + FS_NT * FS_ROWB, sw128_off(r, slot), v);
-                }
             }
         };
         auto fill_x = [&](unsigned char *xt, int item, const long long (&frow)[FS_NPASS], int kc, auto async_tag) {
@@ -304,14 +305,19 @@ fused_sa_fwd_kernel(const FusedFwdArgs a) {
                 default: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
             }
         };
-        if (wres) {                                                // the weight slice, once (a.nslices == 1)
-            for (int kc = 0; kc < nchunks; ++kc) fill_w(base + (size_t)kc * T_BYTES, 0, kc, Async{});
-            if (!X3) {
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-            }
-            fence_async_smem();
-            mbar_arrive(fs_smem(w_full));
+        // weights: ready-made tiles in global memory (fused_sa_wprep_kernel) -> one bulk copy per chunk, issued by one
+        // thread, completing on the consumer's barrier by byte count: the producer warps never touch them
+        auto bulk_w = [&](uint32_t dst, int slice, int kc, uint32_t bar) {
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(a.Wsw) + ((size_t)slice * nchunks + kc) * T_BYTES;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(src), "r"(T_BYTES), "r"(bar)
+                         : "memory");
+        };
+        if (wres && tid == 0) {                                    // the weight slice, once (a.nslices == 1)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fs_smem(w_full)),
+                         "r"((uint32_t)nchunks * T_BYTES)
+                         : "memory");
+            for (int kc = 0; kc < nchunks; ++kc) bulk_w(fs_smem(base + (size_t)kc * T_BYTES), 0, kc, fs_smem(w_full));
         }
         long long cur[FS_NPASS];
         int nxt[FS_NPASS];
@@ -331,14 +337,12 @@ fused_sa_fwd_kernel(const FusedFwdArgs a) {
                 rows_of(item, nxt, cur);
                 if (item + (int)gridDim.x < nitems) load_meta(item + (int)gridDim.x, nxt); // in flight during this item's chunks
                 const int o0 = (item % nsl) * 128;
-                const float *xp[FS_NPASS], *wp[FS_NPASS];
+                const float *xp[FS_NPASS];
                 float4 dp[FS_NPASS];
 #pragma unroll
                 for (int i = 0; i < FS_NPASS; ++i) {
                     const bool live = cur[i] >= 0;
                     xp[i] = live ? a.fT + cur[i] * a.C + slot * 4 : nullptr;
-                    const int o = o0 + i * FS_RPP + rsub;
-                    wp[i] = (!wres && o < a.O) ? a.Wp + (long long)o * a.Kp + slot * 4 : nullptr;
                     dp[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (dp_lane && live) {
                         const float *pp = a.xyz + cur[i] * 3;
@@ -353,7 +357,7 @@ fused_sa_fwd_kernel(const FusedFwdArgs a) {
                     if (pass > 0) mbar_wait(fs_smem(&empty[st]), (uint32_t)((pass - 1) & 1));
                     const uint32_t xs = fs_smem(ring + (size_t)st * slot_bytes);
                     const int k0 = kc * 32 + slot * 4;
-                    const bool featk = k0 + 4 <= a.C, wk = k0 < a.Kp;
+                    const bool featk = k0 + 4 <= a.C;
                     if (kc == kc_dp && dp_lane) {                  // this lane's slot of this chunk is (dp, 0): plain stores
 #pragma unroll
                         for (int i = 0; i < FS_NPASS; ++i) *reinterpret_cast<float4 *>(ring + (size_t)st * slot_bytes + soff[i]) = dp[i];
@@ -364,12 +368,9 @@ fused_sa_fwd_kernel(const FusedFwdArgs a) {
                             cp_async16(xs + soff[i], ok ? xp[i] + kc * 32 : a.fT, ok);
                         }
                     }
-                    if (!wres) {
-#pragma unroll
-                        for (int i = 0; i < FS_NPASS; ++i) {
-                            const bool ok = wk && wp[i] != nullptr;
-                            cp_async16(xs + T_BYTES + soff[i], ok ? wp[i] + kc * 32 : a.Wp, ok);
-                        }
+                    if (!wres && tid == 0) {
+                        asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(fs_smem(&full[st])), "r"(T_BYTES) : "memory");
+                        bulk_w(xs + T_BYTES, o0 >> 7, kc, fs_smem(&full[st]));
                     }
                     if (a.fence_mode == 2) {
                         // the barrier arrival fires when this thread's copies of the chunk have landed: nothing to wait for
@@ -398,7 +399,10 @@ fused_sa_fwd_kernel(const FusedFwdArgs a) {
                     if (pass > 0) mbar_wait(fs_smem(&empty[st]), (uint32_t)((pass - 1) & 1));
                     unsigned char *xt = ring + (size_t)st * slot_bytes;
                     fill_x(xt, item, cur, kc, Async{});
-                    if (!wres) fill_w(xt + T_BYTES, o0, kc, Async{});
+                    if (!wres && tid == 0) {
+                        asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(fs_smem(&full[st])), "r"(T_BYTES) : "memory");
+                        bulk_w(fs_smem(xt + T_BYTES), o0 >> 7, kc, fs_smem(&full[st]));
+                    }
                     publish_slot(st);
                     if (++st == S) { st = 0; ++pass; }
                 }
@@ -587,6 +591,7 @@ static int launch_fused_fwd(FusedFwdArgs &a, cudaStream_t st) {
     const size_t smem = fixed + a.stages * slot + 1024;
     cudaError_t e = cudaFuncSetAttribute(fused_sa_fwd_kernel<NS, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
+    fused_sa_wprep_kernel<X3><<<a.nslices * nchunks, 256, 0, st>>>(a.O, a.Kp, nchunks, a.Wp, const_cast<float *>(a.Wsw));
     const long long ctas = env_ctas > 0 ? env_ctas : kNumSMs;
     fused_sa_fwd_kernel<NS, X3><<<(unsigned)min(a.nitems, ctas), FS_THREADS, smem, st>>>(a);
     return 0;
@@ -598,7 +603,7 @@ using namespace amc3d;
 
 extern "C" int amc3d_fused_sa_forward(int b, int n, int m, int c, int o, int nsample, float radius, int normalize_dp,
                                       int precision, float eps, const float *featT, const float *xyz,
-                                      const float *new_xyz, const int *idx, const float *w_packed,
+                                      const float *new_xyz, const int *idx, const float *w_packed, float *w_tiles,
                                       const float *gamma, const float *beta, float *ysel, unsigned char *arg,
                                       double *sums, float *mean, float *var, float *invstd, float *out,
                                       void *stream) {
@@ -610,7 +615,7 @@ extern "C" int amc3d_fused_sa_forward(int b, int n, int m, int c, int o, int nsa
     if (b == 0 || m == 0) return 0;
     cudaStream_t st = as_stream(stream);
     FusedFwdArgs a;
-    a.fT = featT; a.xyz = xyz; a.qxyz = new_xyz; a.idx = idx; a.Wp = w_packed; a.gamma = gamma;
+    a.fT = featT; a.xyz = xyz; a.qxyz = new_xyz; a.idx = idx; a.Wp = w_packed; a.Wsw = w_tiles; a.gamma = gamma;
     a.ysel = ysel; a.arg = arg; a.gsum = sums; a.gsumsq = sums + o;
     a.B = b; a.N = n; a.M = m; a.C = c; a.O = o; a.Kp = c + 8;
     a.inv_radius = normalize_dp ? 1.0f / radius : 1.0f;

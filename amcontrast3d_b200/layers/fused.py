@@ -71,6 +71,8 @@ class FusedGroupConvBNReLUMax(Function):
         dev = features.device
         fT = transpose_bcn(features)
         wp = pack_weight(weight.detach().float(), C)
+        tiles = ((O + 127) // 128) * ((C + 8 + 31) // 32) * 4096 * (2 if precision == "tf32x3" else 1)
+        wt = torch.empty((tiles,), dtype=torch.float32, device=dev)
         gamma_c, beta_c = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
         ysel = torch.empty((B * M, O), dtype=torch.float32, device=dev)
         arg = torch.empty((B * M, O), dtype=torch.uint8, device=dev)
@@ -82,7 +84,7 @@ class FusedGroupConvBNReLUMax(Function):
         with _capi.guard(features):
             _capi.call("amc3d_fused_sa_forward", B, N, M, C, O, ns, float(radius), int(bool(normalize_dp)),
                        _PREC[precision], float(eps), ptr(fT), ptr(support_xyz), ptr(query_xyz), ptr(idx), ptr(wp),
-                       ptr(gamma_c), ptr(beta_c), ptr(ysel), ptr(arg), ptr(sums), ptr(mean), ptr(var), ptr(invstd),
+                       ptr(wt), ptr(gamma_c), ptr(beta_c), ptr(ysel), ptr(arg), ptr(sums), ptr(mean), ptr(var), ptr(invstd),
                        ptr(out), stream(features))
         ctx.save_for_backward(fT, wp, gamma_c, query_xyz, support_xyz, idx, ysel, arg, mean, invstd, out)
         ctx.cfg = (float(radius), bool(normalize_dp), precision, weight.shape)

@@ -169,6 +169,8 @@ int amc3d_transpose_batched(int b, int rows, int cols, const float *src, float *
  *   xyz (B,N,3) support, new_xyz (B,M,3) queries, idx (B,M,nsample) i32 from amc3d_ball_query
  *   w_packed (O, C+8) = [W[:, 3:3+C] | W[:, 0:3] | 0 0 0 0 0]  (conv weight with the 3 dp columns moved
  *                       behind the features, rows padded to a multiple of 8 floats)
+ *   w_tiles         scratch, ceil(O/128) * ceil((C+8)/32) * 4096 floats (x2 for precision 3): the weights as ready-made
+ *                   swizzled operand tiles, written here and then fetched by one bulk copy per K chunk
  *   precision 1 = TF32 operands (cuDNN's default for the reference's Conv2d), 3 = 3xTF32 (FP32-faithful)
  * Outputs: out (B,O,M); mean/var (O) the batch statistics (var biased, as normalisation uses it);
  * invstd (O); and, kept for the backward: ysel (B*M,O) the pre-normalisation extreme of each (query,
@@ -176,7 +178,7 @@ int amc3d_transpose_batched(int b, int rows, int cols, const float *src, float *
  * Limits: C % 8 == 0, nsample in {16, 32}. */
 int amc3d_fused_sa_forward(int b, int n, int m, int c, int o, int nsample, float radius, int normalize_dp,
                            int precision, float eps, const float *featT, const float *xyz,
-                           const float *new_xyz, const int *idx, const float *w_packed,
+                           const float *new_xyz, const int *idx, const float *w_packed, float *w_tiles,
                            const float *gamma, const float *beta, float *ysel, unsigned char *arg,
                            double *sums, float *mean, float *var, float *invstd, float *out, void *stream);
 
