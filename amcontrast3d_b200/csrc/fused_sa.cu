@@ -25,16 +25,34 @@
 
 namespace amc3d {
 
-constexpr int FS_NT = 128;                 // grouped positions per CTA (UMMA N)
+constexpr int FS_MT = 128;                 // output channels per work item (UMMA M = TMEM lanes)
 constexpr int FS_ROWB = 128;               // bytes per tile row = one swizzle span = 32 floats of K
-constexpr int FS_PW = 8;                   // producer warps (0 .. FS_PW-1); warp FS_PW issues the MMAs; then 4 epilogue warps
+constexpr int FS_PW = 8;                   // producer warps 0 .. FS_PW-1
 constexpr int FS_PROD = FS_PW * 32;        // producer threads
+constexpr int FS_WARP_MMA = FS_PW;         // issues the MMAs
+constexpr int FS_WARP_DP = FS_PW + 1;      // writes the relative-coordinate columns (TF32 path)
+constexpr int FS_WARP_EPI = FS_PW + 2;     // first of the 8 epilogue warps
 constexpr int FS_EPI = 256;                // epilogue threads: two per TMEM lane (each takes every other query of the tile)
 constexpr int FS_RPP = FS_PROD / 8;        // tile rows filled per pass (8 lanes per 128-byte row)
-constexpr int FS_NPASS = FS_NT / FS_RPP;   // passes per 128-row tile
-constexpr int FS_THREADS = FS_PROD + 32 + FS_EPI;
-constexpr int FS_MAX_STAGES = 6;
+constexpr int FS_THREADS = FS_PROD + 64 + FS_EPI;
+constexpr int FS_MAX_STAGES = 8;
 constexpr int FS_REPL = 64;                // replicas of the BatchNorm sums (spreads the atomics over 64x the cache lines)
+
+// n / d for n < 2^31 without a division: q = umulhi(n, m) >> s with m = ceil(2^(31+l) / d), l = ceil(log2 d)
+struct FastDiv {
+    uint32_t m, s, one;
+};
+static inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f{0u, 0u, 1u};
+    if (d <= 1) return f;
+    uint32_t l = 0;
+    while ((1ull << l) < d) ++l;
+    f.m = (uint32_t)(((1ull << (31 + l)) + d - 1) / d);
+    f.s = l - 1;
+    f.one = 0;
+    return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv &f) { return f.one ? n : (__umulhi(n, f.m) >> f.s); }
 
 __device__ __forceinline__ uint32_t fs_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -155,13 +173,13 @@ template <bool X3>
 __global__ void __launch_bounds__(256)
 fused_sa_wprep_kernel(int O, int Kp, int nchunks, const float *__restrict__ Wp, float *__restrict__ Wsw) {
     const int blk = blockIdx.x, j = blk / nchunks, kc = blk % nchunks;
-    unsigned char *dst = reinterpret_cast<unsigned char *>(Wsw) + (size_t)blk * (X3 ? 2 : 1) * FS_NT * FS_ROWB;
-    for (int e = threadIdx.x; e < FS_NT * 8; e += 256) {
+    unsigned char *dst = reinterpret_cast<unsigned char *>(Wsw) + (size_t)blk * (X3 ? 2 : 1) * FS_MT * FS_ROWB;
+    for (int e = threadIdx.x; e < FS_MT * 8; e += 256) {
         const int r = e >> 3, c = e & 7;
         const int o = j * 128 + r, k0 = kc * 32 + c * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (o < O && k0 < Kp) v = __ldg(reinterpret_cast<const float4 *>(Wp + (long long)o * Kp + k0));
-        fs_store<X3>(dst, dst + FS_NT * FS_ROWB, sw128_off(r, c), v);
+        fs_store<X3>(dst, dst + FS_MT * FS_ROWB, sw128_off(r, c), v);
     }
 }
 
@@ -177,43 +195,58 @@ struct FusedFwdArgs {
     float *ysel;            // (B*M, O) pre-normalisation extreme of y over the neighbourhood
     unsigned char *arg;     // (B*M, O) sample index of that extreme (first one)
     double *gsum, *gsumsq;  // FS_REPL x (O) sum y, sum y^2 over all B*M*NS positions (zeroed by the caller)
+    long long *dbg;         // AMC3D_FUSED_DBG: per CTA 12 cycle counters (where each role waits), else NULL
     int B, N, M, C, O, Kp;
     int stages;             // shared-memory ring depth (2..FS_MAX_STAGES)
-    int fence_mode;         // 0: producers fence (generic -> async proxy) before arriving; 1: the MMA thread fences after the wait;
-                            // 2: as 1, and the arrival itself is asynchronous (cp.async.mbarrier.arrive.noinc)
     int w_resident;         // 1: the whole (128 x Kp) weight slice stays in shared memory for the CTA's lifetime
     int nslices;            // ceil(O / 128): output-channel slices per position tile
-    long long nitems;       // position tiles x slices
+    int nitems;             // position tiles x slices
+    FastDiv div_m, div_s;   // division by M (query -> batch) and by nslices (item -> tile)
     float inv_radius;       // 1/radius with normalize_dp, else 1
 };
 
-// Persistent, warp-specialised:  warps 0-7 PRODUCE the operand tiles (ring of `stages` buffers), warp 8 ISSUES the
-// MMAs into one of two TMEM accumulators, warps 9-16 run the EPILOGUE of the previous work item out of the other
-// accumulator.  A work item = (tile of 128 grouped positions, slice of 128 output channels); a CTA takes items
-// blockIdx.x, blockIdx.x + gridDim.x, ...  Barriers: full[s] / empty[s] per ring slot (producers <-> MMA),
-// acc_full[b] / acc_empty[b] per accumulator (MMA <-> epilogue), w_full for the resident weight slice.
+// Persistent, warp-specialised, one CTA per SM.  A work item = (tile of NT grouped positions, slice of 128 output
+// channels); a CTA takes items blockIdx.x, blockIdx.x + gridDim.x, ...  NT = 256 (TF32; the widest UMMA) or 128 (3xTF32).
+//   warps 0-7   PRODUCE the gathered operand: a ring of `stages` slots, one K-chunk (32 floats) of the tile per slot
+//   warp  8     ISSUES the MMAs into one of two TMEM accumulators (one elected lane)
+//   warp  9     TF32 path: computes the relative coordinates (idx -> xyz -> (p - q)/r, a dependent chain of global
+//               loads) ahead of the ring and stores them into the item's last chunk
+//   warps 10-17 run the EPILOGUE of the previous item out of the other accumulator
+// Barriers: full[s] / empty[s] per ring slot (producers <-> MMA), acc_full[b] / acc_empty[b] per accumulator
+// (MMA <-> epilogue), w_full for the resident weight slice.  In the TF32 path a producer thread's arrival on full[s] is
+// asynchronous (cp.async.mbarrier.arrive.noinc): it fires when the thread's copies of the chunk have landed, so nobody
+// waits for them and a chunk reaches the MMA warp as early as it can.
+// The single-thread loops (producer set-up, MMA issue) are latency chains of scalar instructions, so they are kept
+// short: no divisions (FastDiv), 32-bit element offsets, descriptors advanced by additions.
 template <int NS, bool X3>
 __global__ void __launch_bounds__(FS_THREADS, 1)
 fused_sa_fwd_kernel(const FusedFwdArgs a) {
-    constexpr int QPT = FS_NT / NS;                       // queries per tile
-    constexpr uint32_t T_BYTES = (X3 ? 2u : 1u) * FS_NT * FS_ROWB;     // one operand tile (hi [+ lo]): 128 rows x 128 B
+    constexpr int NT = X3 ? 128 : 256;                    // grouped positions per item (UMMA N)
+    constexpr int QPT = NT / NS;                          // queries per tile
+    constexpr int NPASS = NT / FS_RPP;                    // passes of the 256 producer threads over the tile rows
+    constexpr uint32_t XT_BYTES = (X3 ? 2u : 1u) * NT * FS_ROWB;       // one gathered chunk (hi [+ lo]): NT rows x 128 B
+    constexpr uint32_t WT_BYTES = (X3 ? 2u : 1u) * FS_MT * FS_ROWB;    // one weight chunk: 128 rows x 128 B
     extern __shared__ __align__(1024) unsigned char fs_smem_raw[];
     // the runtime only guarantees 16-byte alignment of dynamic shared memory: align by hand
     unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(fs_smem_raw) + 1023) & ~(uintptr_t)1023);
-    __shared__ __align__(8) uint64_t bars[2 * FS_MAX_STAGES + 5];
+    __shared__ __align__(8) uint64_t bars[2 * FS_MAX_STAGES + 9];
     __shared__ uint32_t tmem_base_s;
     const int S = a.stages;
     const int nchunks = (a.Kp + 31) / 32;
     const bool wres = a.w_resident != 0;
     // layout: [resident W: nchunks tiles] then the ring; a ring slot is [X tile] or [X tile | W tile]
-    unsigned char *ring = base + (wres ? (size_t)nchunks * T_BYTES : 0);
-    const uint32_t slot_bytes = wres ? T_BYTES : 2 * T_BYTES;
+    unsigned char *ring = base + (wres ? (size_t)nchunks * WT_BYTES : 0);
+    const uint32_t slot_bytes = wres ? XT_BYTES : XT_BYTES + WT_BYTES;
     uint64_t *full = bars, *empty = bars + FS_MAX_STAGES, *acc_full = bars + 2 * FS_MAX_STAGES,
-             *acc_empty = bars + 2 * FS_MAX_STAGES + 2, *w_full = bars + 2 * FS_MAX_STAGES + 4;
+             *acc_empty = bars + 2 * FS_MAX_STAGES + 2, *w_full = bars + 2 * FS_MAX_STAGES + 4,
+             *dp_ready = bars + 2 * FS_MAX_STAGES + 5, *dp_free = bars + 2 * FS_MAX_STAGES + 7;
+    // TF32 path: two staging buffers of NT float4 (dp, 0) behind the ring, filled by the dp warp one or two items ahead
+    float4 *dp_stage = reinterpret_cast<float4 *>(ring + (size_t)S * slot_bytes);
 
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int Q = a.B * a.M;                               // queries (host checks B*M < 2^31)
-    const int nitems = (int)a.nitems, nsl = a.nslices;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Q = a.B * a.M;                               // queries (host checks B*M < 2^25)
+    const int nitems = a.nitems, nsl = a.nslices;
+    const int kc_dp = a.C >> 5, dp_slot = (a.C & 31) >> 2; // chunk and 16-byte slot that hold (dp, 0): C % 4 == 0
 
     if (tid == 0) {
         for (int s = 0; s < FS_MAX_STAGES; ++s) {
@@ -225,11 +258,15 @@ fused_sa_fwd_kernel(const FusedFwdArgs a) {
             mbar_init(fs_smem(&acc_empty[b]), FS_EPI);             // every epilogue thread arrives
         }
         mbar_init(fs_smem(w_full), 1);                             // one arrive.expect_tx; the bulk copies complete it
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(fs_smem(&dp_ready[b]), 32);                  // the dp warp's lanes
+            mbar_init(fs_smem(&dp_free[b]), 32);                   // the 32 producer threads of the (dp, 0) column
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == FS_PW) {                                           // TMEM: two accumulators of 128 lanes x 128 columns
+    if (warp == FS_WARP_MMA) {                                     // TMEM: two accumulators of 128 lanes x NT columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(fs_smem(&tmem_base_s)),
-                     "r"(256u)
+                     "r"((uint32_t)(2 * NT))
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -241,222 +278,243 @@ fused_sa_fwd_kernel(const FusedFwdArgs a) {
     if (warp < FS_PW) {
         // ================================================================== producers
         const int slot = tid & 7, rsub = tid >> 3;                 // 8 lanes per 128-byte row, FS_RPP rows per pass
-        // neighbour index of the grouped positions this thread fetches in an item (raw loads: nothing may depend on
-        // them until the item starts, so that they are in flight during the previous item's chunks)
-        auto load_meta = [&](int item, int (&nidx)[FS_NPASS]) {
-            const int q0 = (item / nsl) * QPT;
+        // rows rsub + 32 i share (row & 7): one swizzled offset, passes 4096 bytes apart
+        const uint32_t soff0 = sw128_off(rsub, slot);
+        // neighbour index of the positions this thread fetches in an item, -1 past the end (raw loads: nothing depends
+        // on them until the item starts, so they are in flight during the previous item's chunks)
+        auto load_idx = [&](int item, int (&nidx)[NPASS]) {
+            const int q0 = (int)fdiv((uint32_t)item, a.div_s) * QPT;
 #pragma unroll
-            for (int i = 0; i < FS_NPASS; ++i) {
+            for (int i = 0; i < NPASS; ++i) {
                 const int r = i * FS_RPP + rsub;
                 const int qg = q0 + r / NS;
-                nidx[i] = qg < Q ? __ldg(a.idx + (long long)qg * NS + (r % NS)) : 0;
-            }
-        };
-        // support row (b*N + n) per position, -1 past the end
-        auto rows_of = [&](int item, const int (&nidx)[FS_NPASS], long long (&frow)[FS_NPASS]) {
-            const int q0 = (item / nsl) * QPT;
-#pragma unroll
-            for (int i = 0; i < FS_NPASS; ++i) {
-                const int qg = q0 + (i * FS_RPP + rsub) / NS;
-                frow[i] = qg < Q ? (long long)(qg / a.M) * a.N + nidx[i] : -1;
-            }
-        };
-        auto fill_x = [&](unsigned char *xt, int item, const long long (&frow)[FS_NPASS], int kc, auto async_tag) {
-            constexpr bool ASYNC = decltype(async_tag)::value;
-            const long long q0 = (long long)(item / nsl) * QPT;
-            const int k0 = kc * 32 + slot * 4;
-#pragma unroll
-            for (int i = 0; i < FS_NPASS; ++i) {
-                const int r = i * FS_RPP + rsub;
-                const bool live = frow[i] >= 0;
-                const bool feat = live && k0 + 4 <= a.C;
-                const bool isdp = live && k0 == a.C;
-                if (ASYNC && !isdp) {
-                    cp_async16(fs_smem(xt) + sw128_off(r, slot), feat ? a.fT + frow[i] * a.C + k0 : a.fT, feat);
-                    continue;
-                }
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (feat) {
-                    v = __ldg(reinterpret_cast<const float4 *>(a.fT + frow[i] * a.C + k0));
-                } else if (isdp) {
-                    const float *pp = a.xyz + frow[i] * 3;
-                    const float *qq = a.qxyz + (q0 + r / NS) * 3;
-                    v.x = (__ldg(pp) - __ldg(qq)) * a.inv_radius;
-                    v.y = (__ldg(pp + 1) - __ldg(qq + 1)) * a.inv_radius;
-                    v.z = (__ldg(pp + 2) - __ldg(qq + 2)) * a.inv_radius;
-                }
-                fs_store<X3>(xt, xt + FS_NT * FS_ROWB, sw128_off(r, slot), v);
-            }
-        };
-        using Async = std::integral_constant<bool, !X3>;           // TF32: cp.async ring; 3xTF32: through registers
-        // hand chunk `c` (global chunk counter) to the MMA warp
-        auto publish_slot = [&](int slot_i) {
-            if (a.fence_mode == 0) fence_async_smem();             // generic-proxy writes -> visible to the MMA (async proxy)
-            mbar_arrive(fs_smem(&full[slot_i]));
-        };
-        auto publish = [&](long long c) { publish_slot((int)(c % S)); };
-        auto wait_groups = [&](int n) {                            // cp.async.wait_group needs an immediate
-            switch (n) {
-                case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-                case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-                case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-                case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-                case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
-                default: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+                nidx[i] = qg < Q ? __ldg(a.idx + (long long)qg * NS + (r % NS)) : -1;
             }
         };
         // weights: ready-made tiles in global memory (fused_sa_wprep_kernel) -> one bulk copy per chunk, issued by one
         // thread, completing on the consumer's barrier by byte count: the producer warps never touch them
         auto bulk_w = [&](uint32_t dst, int slice, int kc, uint32_t bar) {
-            const unsigned char *src = reinterpret_cast<const unsigned char *>(a.Wsw) + ((size_t)slice * nchunks + kc) * T_BYTES;
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(a.Wsw) + ((size_t)slice * nchunks + kc) * WT_BYTES;
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst), "l"(src), "r"(T_BYTES), "r"(bar)
+                         ::"r"(dst), "l"(src), "r"(WT_BYTES), "r"(bar)
                          : "memory");
         };
         if (wres && tid == 0) {                                    // the weight slice, once (a.nslices == 1)
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fs_smem(w_full)),
-                         "r"((uint32_t)nchunks * T_BYTES)
+                         "r"((uint32_t)nchunks * WT_BYTES)
                          : "memory");
-            for (int kc = 0; kc < nchunks; ++kc) bulk_w(fs_smem(base + (size_t)kc * T_BYTES), 0, kc, fs_smem(w_full));
+            for (int kc = 0; kc < nchunks; ++kc) bulk_w(fs_smem(base + (size_t)kc * WT_BYTES), 0, kc, fs_smem(w_full));
         }
-        long long cur[FS_NPASS];
-        int nxt[FS_NPASS];
-        long long c = 0;                                           // chunks issued so far
-        if ((int)blockIdx.x < nitems) load_meta((int)blockIdx.x, nxt);
-        if (!X3) {
-            // TF32: the hot loop is one predicated 16-byte cp.async per row and chunk.  Everything that does not
-            // change per chunk is hoisted: swizzled destination offsets (per kernel), row pointers and the
-            // relative coordinates (per item; their loads are in flight while the feature chunks are issued).
-            uint32_t soff[FS_NPASS];
+        // the thread that announces a chunk's weight bytes (expect_tx) must arrive on the same barrier afterwards, or the
+        // phase could complete before the announcement: pick one that is never the (dp, 0) slot
+        const int wtid = X3 ? 0 : ((dp_slot + 1) & 7);
+        int nxt[NPASS];
+        if ((int)blockIdx.x < nitems) load_idx((int)blockIdx.x, nxt);
+        int st = 0, pass = 0;                                      // ring slot of the next chunk and the ring's pass count
+        long long t_we = 0, t_set = 0;
+        const long long t_begin = a.dbg ? clock64() : 0;
+        int itl = 0;                                               // items done by this CTA
+        for (int item = blockIdx.x; item < nitems; item += (int)gridDim.x, ++itl) {
+            const long long ts0 = a.dbg ? clock64() : 0;
+            const uint32_t tile = fdiv((uint32_t)item, a.div_s);
+            const int sl = item - (int)tile * nsl;
+            const int q0 = (int)tile * QPT;
+            // element offset of this thread's 16 bytes in each of its rows (host checks B*N*C < 2^31)
+            uint32_t xoff[NPASS];
+            uint32_t rowv[X3 ? NPASS : 1];                         // support row b*N + n (3xTF32 path: coordinates inline)
+            uint32_t livemask = 0;
 #pragma unroll
-            for (int i = 0; i < FS_NPASS; ++i) soff[i] = sw128_off(i * FS_RPP + rsub, slot);
-            int st = 0, pass = 0;
-            const int kc_dp = a.C / 32;                            // chunk and slot that hold (dp, 0): C % 4 == 0
-            const bool dp_lane = slot == (a.C % 32) / 4;
-            for (int item = blockIdx.x; item < nitems; item += (int)gridDim.x) {
-                rows_of(item, nxt, cur);
-                if (item + (int)gridDim.x < nitems) load_meta(item + (int)gridDim.x, nxt); // in flight during this item's chunks
-                const int o0 = (item % nsl) * 128;
-                const float *xp[FS_NPASS];
-                float4 dp[FS_NPASS];
-#pragma unroll
-                for (int i = 0; i < FS_NPASS; ++i) {
-                    const bool live = cur[i] >= 0;
-                    xp[i] = live ? a.fT + cur[i] * a.C + slot * 4 : nullptr;
-                    dp[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (dp_lane && live) {
-                        const float *pp = a.xyz + cur[i] * 3;
-                        const float *qq = a.qxyz + ((long long)(item / nsl) * QPT + (i * FS_RPP + rsub) / NS) * 3;
-                        dp[i].x = (__ldg(pp) - __ldg(qq)) * a.inv_radius;
-                        dp[i].y = (__ldg(pp + 1) - __ldg(qq + 1)) * a.inv_radius;
-                        dp[i].z = (__ldg(pp + 2) - __ldg(qq + 2)) * a.inv_radius;
-                    }
-                }
-                for (int kc = 0; kc < nchunks; ++kc, ++c) {
-                    // ring position without divisions: chunk c sits in slot st on pass `pass` of the ring
-                    if (pass > 0) mbar_wait(fs_smem(&empty[st]), (uint32_t)((pass - 1) & 1));
-                    const uint32_t xs = fs_smem(ring + (size_t)st * slot_bytes);
-                    const int k0 = kc * 32 + slot * 4;
+            for (int i = 0; i < NPASS; ++i) {
+                const int qg = q0 + (i * FS_RPP + rsub) / NS;
+                const uint32_t bb = fdiv((uint32_t)qg, a.div_m);
+                const bool live = nxt[i] >= 0;
+                const uint32_t row = live ? bb * (uint32_t)a.N + (uint32_t)nxt[i] : 0u;
+                xoff[i] = row * (uint32_t)a.C + (uint32_t)(slot * 4);
+                if (X3) rowv[i] = row;
+                livemask |= (live ? 1u : 0u) << i;
+            }
+            if (item + (int)gridDim.x < nitems) load_idx(item + (int)gridDim.x, nxt);   // in flight during this item's chunks
+            if (a.dbg) t_set += clock64() - ts0;
+            for (int kc = 0; kc < nchunks; ++kc) {
+                const long long tw0 = a.dbg ? clock64() : 0;
+                if (pass > 0) mbar_wait(fs_smem(&empty[st]), (uint32_t)((pass - 1) & 1));
+                if (a.dbg) t_we += clock64() - tw0;
+                unsigned char *xt = ring + (size_t)st * slot_bytes;
+                const uint32_t xs = fs_smem(xt);
+                const int k0 = kc * 32 + slot * 4;
+                if (!X3) {
+                    // TF32: predicated 16-byte cp.async per row straight into the swizzled tile (zero-fill past the
+                    // features and for dead rows); the (dp, 0) slot of the last chunk belongs to the dp warp
                     const bool featk = k0 + 4 <= a.C;
-                    if (kc == kc_dp && dp_lane) {                  // this lane's slot of this chunk is (dp, 0): plain stores
+                    if (kc == kc_dp && slot == dp_slot) {
+                        const int sb = itl & 1;
+                        mbar_wait(fs_smem(&dp_ready[sb]), (uint32_t)((itl >> 1) & 1));
 #pragma unroll
-                        for (int i = 0; i < FS_NPASS; ++i) *reinterpret_cast<float4 *>(ring + (size_t)st * slot_bytes + soff[i]) = dp[i];
+                        for (int i = 0; i < NPASS; ++i)
+                            *reinterpret_cast<float4 *>(xt + soff0 + (uint32_t)i * (FS_RPP * FS_ROWB)) = dp_stage[sb * NT + i * FS_RPP + rsub];
+                        mbar_arrive(fs_smem(&dp_free[sb]));
                     } else {
 #pragma unroll
-                        for (int i = 0; i < FS_NPASS; ++i) {
-                            const bool ok = featk && xp[i] != nullptr;
-                            cp_async16(xs + soff[i], ok ? xp[i] + kc * 32 : a.fT, ok);
+                        for (int i = 0; i < NPASS; ++i) {
+                            const bool ok = featk && ((livemask >> i) & 1u);
+                            cp_async16(xs + soff0 + (uint32_t)i * (FS_RPP * FS_ROWB), a.fT + xoff[i] + kc * 32, ok);
                         }
                     }
-                    if (!wres && tid == 0) {
-                        asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(fs_smem(&full[st])), "r"(T_BYTES) : "memory");
-                        bulk_w(xs + T_BYTES, o0 >> 7, kc, fs_smem(&full[st]));
-                    }
-                    if (a.fence_mode == 2) {
-                        // the barrier arrival fires when this thread's copies of the chunk have landed: nothing to wait for
-                        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(fs_smem(&full[st])) : "memory");
-                    } else {
-                        asm volatile("cp.async.commit_group;" ::: "memory");
-                        if (c >= S - 1) {                          // all but the newest S-1 groups have landed:
-                            wait_groups(S - 1);                    // chunk c - (S-1), which sits in the NEXT slot
-                            publish_slot(st + 1 == S ? 0 : st + 1);
+                } else {
+                    // 3xTF32: through registers (split into hi = rna(x) and lo = x - hi), relative coordinates inline
+#pragma unroll
+                    for (int i = 0; i < NPASS; ++i) {
+                        const int r = i * FS_RPP + rsub;
+                        const bool live = (livemask >> i) & 1u;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (live && k0 + 4 <= a.C) {
+                            v = __ldg(reinterpret_cast<const float4 *>(a.fT + xoff[i] + kc * 32));
+                        } else if (live && k0 == a.C) {
+                            const float *pp = a.xyz + (size_t)rowv[X3 ? i : 0] * 3;
+                            const float *qq = a.qxyz + (size_t)(q0 + r / NS) * 3;
+                            v.x = (__ldg(pp) - __ldg(qq)) * a.inv_radius;
+                            v.y = (__ldg(pp + 1) - __ldg(qq + 1)) * a.inv_radius;
+                            v.z = (__ldg(pp + 2) - __ldg(qq + 2)) * a.inv_radius;
                         }
+                        fs_store<X3>(xt, xt + NT * FS_ROWB, sw128_off(r, slot), v);
                     }
-                    if (++st == S) { st = 0; ++pass; }
                 }
-            }
-            if (a.fence_mode != 2) {                               // drain the ring
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-                for (long long d = (c >= S - 1 ? c - (S - 1) : 0); d < c; ++d) publish_slot((int)(d % S));
-            }
-        } else {
-            int st = 0, pass = 0;
-            for (int item = blockIdx.x; item < nitems; item += (int)gridDim.x) {
-                rows_of(item, nxt, cur);
-                if (item + (int)gridDim.x < nitems) load_meta(item + (int)gridDim.x, nxt);
-                const int o0 = (item % nsl) * 128;
-                for (int kc = 0; kc < nchunks; ++kc, ++c) {
-                    if (pass > 0) mbar_wait(fs_smem(&empty[st]), (uint32_t)((pass - 1) & 1));
-                    unsigned char *xt = ring + (size_t)st * slot_bytes;
-                    fill_x(xt, item, cur, kc, Async{});
-                    if (!wres && tid == 0) {
-                        asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(fs_smem(&full[st])), "r"(T_BYTES) : "memory");
-                        bulk_w(fs_smem(xt + T_BYTES), o0 >> 7, kc, fs_smem(&full[st]));
-                    }
-                    publish_slot(st);
-                    if (++st == S) { st = 0; ++pass; }
+                if (!wres && tid == wtid) {
+                    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(fs_smem(&full[st])), "r"(WT_BYTES) : "memory");
+                    bulk_w(xs + XT_BYTES, sl, kc, fs_smem(&full[st]));
                 }
+                if (!X3) {
+                    // the arrival fires when this thread's copies have landed; the 32 threads that wrote the (dp, 0) column
+                    // with plain stores have none in flight and arrive in the ordinary (release) way
+                    if (kc == kc_dp && slot == dp_slot) mbar_arrive(fs_smem(&full[st]));
+                    else asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(fs_smem(&full[st])) : "memory");
+                } else {
+                    fence_async_smem();                            // generic-proxy stores -> visible to the MMA (async proxy)
+                    mbar_arrive(fs_smem(&full[st]));
+                }
+                if (++st == S) { st = 0; ++pass; }
             }
         }
-    } else if (warp == FS_PW) {
+        if (a.dbg && tid == 0) {
+            a.dbg[blockIdx.x * 12 + 0] = clock64() - t_begin;
+            a.dbg[blockIdx.x * 12 + 1] = t_we;
+            a.dbg[blockIdx.x * 12 + 2] = t_set;
+        }
+    } else if (warp == FS_WARP_MMA) {
         // ================================================================== MMA issuer (one elected lane)
-        const uint32_t idesc = umma_idesc_tf32(128, FS_NT);
+        const uint32_t idesc = umma_idesc_tf32(FS_MT, NT);
         if (wres) {
             mbar_wait(fs_smem(w_full), 0);
             tc_fence_after();
         }
-        long long it = 0;
-        int st = 0;
+        int it = 0, st = 0;
         uint32_t ph = 0;                                           // ring slot and its phase parity, kept incrementally
+        long long t_wf = 0, t_wa = 0, t_iss = 0;
+        const long long t_begin = a.dbg ? clock64() : 0;
+        const uint32_t ring_s = fs_smem(ring), wres_s = fs_smem(base);
+        const uint64_t desc_hi = umma_desc_sw128(0);               // everything but the 14-bit start address
         for (int item = blockIdx.x; item < nitems; item += (int)gridDim.x, ++it) {
-            const int buf = (int)(it & 1);
+            const int buf = it & 1;
+            const long long ta0 = a.dbg ? clock64() : 0;
             mbar_wait(fs_smem(&acc_empty[buf]), (uint32_t)(((it >> 1) & 1) ^ 1));   // the epilogue has drained this accumulator
-            tc_fence_after();
-            const uint32_t d = tmem_base + (uint32_t)(buf * 128);
+            if (a.dbg) t_wa += clock64() - ta0;
+            const uint32_t d = tmem_base + (uint32_t)(buf * NT);
             for (int kc = 0; kc < nchunks; ++kc) {
+                const long long tf0 = a.dbg ? clock64() : 0;
                 mbar_wait(fs_smem(&full[st]), ph);
-                if (a.fence_mode != 0) fence_async_smem();
-                tc_fence_after();
-                if ((tid & 31) == 0) {
-                    const uint32_t xs = fs_smem(ring + (size_t)st * slot_bytes);
-                    const uint32_t ws = wres ? fs_smem(base + (size_t)kc * T_BYTES) : xs + T_BYTES;
-                    const uint32_t xl = xs + FS_NT * FS_ROWB, wl = ws + FS_NT * FS_ROWB;     // X3 only
-                    const int ksteps = min(4, (a.Kp - kc * 32) / 8);
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        const uint32_t acc = (kc > 0 || ks > 0) ? 1u : 0u;
-                        const uint64_t da = umma_desc_sw128(ws + ks * 32), db = umma_desc_sw128(xs + ks * 32);
-                        if (X3) {
-                            umma_tf32(d, umma_desc_sw128(wl + ks * 32), db, idesc, acc);    // lo * hi
-                            umma_tf32(d, da, umma_desc_sw128(xl + ks * 32), idesc, 1u);     // hi * lo
-                            umma_tf32(d, da, db, idesc, 1u);                                 // hi * hi
-                        } else {
-                            umma_tf32(d, da, db, idesc, acc);
+                if (a.dbg) t_wf += clock64() - tf0;
+                const long long ti0 = a.dbg ? clock64() : 0;
+                if (lane == 0) {
+                    fence_async_smem();                            // the chunk was written through the generic proxy
+                    tc_fence_after();
+                    const uint32_t xs = ring_s + (uint32_t)st * slot_bytes;
+                    const uint32_t ws = wres ? wres_s + (uint32_t)kc * WT_BYTES : xs + XT_BYTES;
+                    // descriptors differ in the start-address field only: (addr >> 4), +2 per k-step of 32 bytes
+                    const uint64_t db0 = desc_hi | (uint64_t)((xs & 0x3FFFF) >> 4), da0 = desc_hi | (uint64_t)((ws & 0x3FFFF) >> 4);
+                    const int ksteps = min(4, (a.Kp - kc * 32) >> 3);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        if (ks < ksteps) {
+                            const uint32_t acc = (kc | ks) != 0 ? 1u : 0u;
+                            const uint64_t da = da0 + (uint64_t)(2 * ks), db = db0 + (uint64_t)(2 * ks);
+                            if (X3) {
+                                constexpr uint64_t XLO = (uint64_t)((NT * FS_ROWB) >> 4), WLO = (uint64_t)((FS_MT * FS_ROWB) >> 4);
+                                umma_tf32(d, da + WLO, db, idesc, acc);                     // lo * hi
+                                umma_tf32(d, da, db + XLO, idesc, 1u);                      // hi * lo
+                                umma_tf32(d, da, db, idesc, 1u);                            // hi * hi
+                            } else {
+                                umma_tf32(d, da, db, idesc, acc);
+                            }
                         }
                     }
                     umma_commit(fs_smem(&empty[st]));               // frees the ring slot once these MMAs have read it
                     if (kc == nchunks - 1) umma_commit(fs_smem(&acc_full[buf]));
                 }
                 __syncwarp();
+                if (a.dbg) t_iss += clock64() - ti0;
                 if (++st == S) { st = 0; ph ^= 1u; }
             }
         }
+        if (a.dbg && lane == 0) {
+            a.dbg[blockIdx.x * 12 + 4] = clock64() - t_begin;
+            a.dbg[blockIdx.x * 12 + 5] = t_wf;
+            a.dbg[blockIdx.x * 12 + 6] = t_wa;
+            a.dbg[blockIdx.x * 12 + 7] = t_iss;
+        }
         tc_fence_before();
+    } else if (warp == FS_WARP_DP) {
+        // ================================================================== relative coordinates (TF32 path)
+        // idx -> xyz is a dependent chain of global loads.  This warp walks it for the item's NT positions — the indices
+        // were fetched one item earlier — and leaves (dp, 0) in one of two staging buffers, up to two items ahead of the
+        // ring; the 32 producer threads that own that 16-byte column move it into the item's last chunk.
+        // (dp_ready / dp_free are an ordinary double-buffer handshake: each side is at most one phase from the other.)
+        if (!X3) {
+            long long t_wd = 0;
+            int nidx[NPASS];
+            auto load_idx = [&](int item) {
+                const int q0 = (int)fdiv((uint32_t)item, a.div_s) * QPT;
+#pragma unroll
+                for (int j = 0; j < NPASS; ++j) {
+                    const int r = j * 32 + lane;
+                    const int qg = q0 + r / NS;
+                    nidx[j] = qg < Q ? __ldg(a.idx + (long long)qg * NS + (r % NS)) : -1;
+                }
+            };
+            if ((int)blockIdx.x < nitems) load_idx((int)blockIdx.x);
+            int itl = 0;
+            for (int item = blockIdx.x; item < nitems; item += (int)gridDim.x, ++itl) {
+                const int q0 = (int)fdiv((uint32_t)item, a.div_s) * QPT;
+                float4 dp[NPASS];
+#pragma unroll
+                for (int j = 0; j < NPASS; ++j) {
+                    const int qg = q0 + (j * 32 + lane) / NS;
+                    dp[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (nidx[j] >= 0) {
+                        const uint32_t bb = fdiv((uint32_t)qg, a.div_m);
+                        const float *pp = a.xyz + ((size_t)bb * a.N + nidx[j]) * 3;
+                        const float *qq = a.qxyz + (size_t)qg * 3;
+                        dp[j].x = (__ldg(pp) - __ldg(qq)) * a.inv_radius;
+                        dp[j].y = (__ldg(pp + 1) - __ldg(qq + 1)) * a.inv_radius;
+                        dp[j].z = (__ldg(pp + 2) - __ldg(qq + 2)) * a.inv_radius;
+                    }
+                }
+                if (item + (int)gridDim.x < nitems) load_idx(item + (int)gridDim.x);
+                const int sb = itl & 1;
+                const long long td0 = a.dbg ? clock64() : 0;
+                if (itl >= 2) mbar_wait(fs_smem(&dp_free[sb]), (uint32_t)(((itl >> 1) - 1) & 1));   // item itl - 2 has been moved out
+                if (a.dbg) t_wd += clock64() - td0;
+#pragma unroll
+                for (int j = 0; j < NPASS; ++j) dp_stage[sb * NT + j * 32 + lane] = dp[j];
+                mbar_arrive(fs_smem(&dp_ready[sb]));
+            }
+            if (a.dbg && lane == 0) a.dbg[blockIdx.x * 12 + 3] = t_wd;
+        }
     } else {
         // ================================================================== epilogue: a thread owns one channel lane and
         // every other query of the tile (two threads per lane)
         const int quad = warp & 3;                                 // TMEM lane quadrant this warp may read
-        const int half = (warp - (FS_PW + 1)) >> 2;                // which queries of the tile: qi % 2 == half
-        const int lane_o = quad * 32 + (tid & 31);
+        const int half = (warp - FS_WARP_EPI) >> 2;                // which queries of the tile: qi % 2 == half
+        const int lane_o = quad * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
         float csum = 0.f, csq = 0.f;                               // BatchNorm sums of channel `co`, flushed when it changes
         int co = -1;
@@ -469,21 +527,26 @@ fused_sa_fwd_kernel(const FusedFwdArgs a) {
             csum = 0.f;
             csq = 0.f;
         };
-        long long it = 0;
+        int it = 0;
+        long long t_wacc = 0;
+        const long long t_begin = a.dbg ? clock64() : 0;
         for (int item = blockIdx.x; item < nitems; item += (int)gridDim.x, ++it) {
-            const int buf = (int)(it & 1);
-            const int q0 = (item / nsl) * QPT;
-            const int o = (item % nsl) * 128 + lane_o;
+            const int buf = it & 1;
+            const uint32_t tile = fdiv((uint32_t)item, a.div_s);
+            const int q0 = (int)tile * QPT;
+            const int o = (item - (int)tile * nsl) * FS_MT + lane_o;
             if (o != co) { flush(); co = o; }
             const bool live = o < a.O;
             // gamma < 0: BatchNorm + ReLU decrease in y, the pooled maximum sits at the MINIMUM of y: track max of -y
             const float sgn = (live && __ldg(a.gamma + o) < 0.f) ? -1.f : 1.f;
+            const long long te0 = a.dbg ? clock64() : 0;
             mbar_wait(fs_smem(&acc_full[buf]), (uint32_t)((it >> 1) & 1));
+            if (a.dbg) t_wacc += clock64() - te0;
             tc_fence_after();
 #pragma unroll 1
             for (int qi = half; qi < QPT; qi += 2) {
                 float v[NS];
-                tmem_ld_query<NS>(lane_addr + (uint32_t)(buf * 128 + qi * NS), v);   // warp-uniform control flow up to here
+                tmem_ld_query<NS>(lane_addr + (uint32_t)(buf * NT + qi * NS), v);   // warp-uniform control flow up to here
                 // two independent (max, arg-max) chains over the halves, four partial sums: no branches, short chains
                 float m0 = v[0] * sgn, m1 = v[NS / 2] * sgn;
                 int i0 = 0, i1 = NS / 2;
@@ -517,11 +580,15 @@ fused_sa_fwd_kernel(const FusedFwdArgs a) {
             mbar_arrive(fs_smem(&acc_empty[buf]));                 // the MMA warp may overwrite this accumulator
         }
         flush();
+        if (a.dbg && tid == FS_WARP_EPI * 32) {
+            a.dbg[blockIdx.x * 12 + 8] = clock64() - t_begin;
+            a.dbg[blockIdx.x * 12 + 9] = t_wacc;
+        }
     }
     __syncthreads();
-    if (warp == FS_PW) {
+    if (warp == FS_WARP_MMA) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * NT)) : "memory");
     }
 }
 
@@ -575,25 +642,47 @@ static int launch_fused_fwd(FusedFwdArgs &a, cudaStream_t st) {
     static const int env_st = getenv("AMC3D_FUSED_STAGES") ? atoi(getenv("AMC3D_FUSED_STAGES")) : 0;
     static const int env_wres = getenv("AMC3D_FUSED_WRES") ? atoi(getenv("AMC3D_FUSED_WRES")) : 1;
     static const int env_ctas = getenv("AMC3D_FUSED_CTAS") ? atoi(getenv("AMC3D_FUSED_CTAS")) : 0;
-    static const int env_fence = getenv("AMC3D_FUSED_FENCE") ? atoi(getenv("AMC3D_FUSED_FENCE")) : 0;
-    a.fence_mode = X3 ? min(env_fence, 1) : env_fence;
-    const size_t tile = (size_t)(X3 ? 2 : 1) * FS_NT * FS_ROWB;
-    const size_t budget = 200 * 1024;                               // of the 227 KB a CTA may own: one persistent CTA per SM
+    static const int env_kb = getenv("AMC3D_FUSED_KB") ? atoi(getenv("AMC3D_FUSED_KB")) : 212;
+    static const bool env_dbg = getenv("AMC3D_FUSED_DBG") != nullptr;
+    constexpr int NT = X3 ? 128 : 256;                              // as in the kernel
+    const size_t xt = (size_t)(X3 ? 2 : 1) * NT * FS_ROWB, wt = (size_t)(X3 ? 2 : 1) * FS_MT * FS_ROWB;
+    const size_t budget = (size_t)env_kb * 1024;                    // of the 227 KB a CTA may own: one persistent CTA per SM
     const int nchunks = (a.Kp + 31) / 32;
-    a.nslices = div_up(a.O, 128);
-    a.nitems = div_up_ll((long long)a.B * a.M, FS_NT / NS) * a.nslices;
+    a.nslices = div_up(a.O, FS_MT);
+    a.nitems = (int)(div_up_ll((long long)a.B * a.M, NT / NS) * a.nslices);
+    a.div_m = make_fastdiv((uint32_t)a.M);
+    a.div_s = make_fastdiv((uint32_t)a.nslices);
     // a single output-channel slice whose weights leave room for >= 3 ring slots: keep them resident
-    a.w_resident = (env_wres && a.nslices == 1 && nchunks * tile + 3 * tile <= budget) ? 1 : 0;
-    const size_t fixed = a.w_resident ? nchunks * tile : 0, slot = a.w_resident ? tile : 2 * tile;
+    a.w_resident = (env_wres && a.nslices == 1 && nchunks * wt + 3 * xt <= budget) ? 1 : 0;
+    const size_t fixed = a.w_resident ? nchunks * wt : 0, slot = a.w_resident ? xt : xt + wt;
     a.stages = (int)min((size_t)FS_MAX_STAGES, (budget - fixed) / slot);
     if (env_st >= 2 && env_st <= a.stages) a.stages = env_st;
     if (a.stages < 2) return (int)cudaErrorInvalidConfiguration;
-    const size_t smem = fixed + a.stages * slot + 1024;
+    const size_t smem = fixed + a.stages * slot + 1024 + (X3 ? 0 : 2 * NT * sizeof(float4));   // + alignment slack + dp staging
     cudaError_t e = cudaFuncSetAttribute(fused_sa_fwd_kernel<NS, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     fused_sa_wprep_kernel<X3><<<a.nslices * nchunks, 256, 0, st>>>(a.O, a.Kp, nchunks, a.Wp, const_cast<float *>(a.Wsw));
-    const long long ctas = env_ctas > 0 ? env_ctas : kNumSMs;
-    fused_sa_fwd_kernel<NS, X3><<<(unsigned)min(a.nitems, ctas), FS_THREADS, smem, st>>>(a);
+    static long long *dbg_dev = nullptr;
+    a.dbg = nullptr;
+    if (env_dbg) {
+        if (!dbg_dev) cudaMalloc(&dbg_dev, sizeof(long long) * 12 * 1024);
+        cudaMemsetAsync(dbg_dev, 0, sizeof(long long) * 12 * 1024, st);
+        a.dbg = dbg_dev;
+    }
+    const unsigned grid = (unsigned)min(a.nitems, env_ctas > 0 ? env_ctas : kNumSMs);
+    fused_sa_fwd_kernel<NS, X3><<<grid, FS_THREADS, smem, st>>>(a);
+    if (env_dbg) {                                                  // development aid: cycles per role, averaged over the CTAs
+        static long long h[12 * 1024];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, dbg_dev, sizeof(long long) * 12 * grid, cudaMemcpyDeviceToHost);
+        double avg[12] = {0};
+        for (unsigned b = 0; b < grid; ++b)
+            for (int k = 0; k < 12; ++k) avg[k] += (double)h[b * 12 + k] / grid;
+        fprintf(stderr, "[fused dbg] C=%d O=%d NT=%d items/CTA=%.1f chunks=%d S=%d wres=%d | producer total %.0f wait_empty %.0f setup %.0f | dp warp wait_free %.0f | "
+                        "mma total %.0f wait_full %.0f wait_acc_empty %.0f issue %.0f | epilogue total %.0f wait_acc_full %.0f\n",
+                a.C, a.O, NT, (double)a.nitems / grid, nchunks, a.stages, a.w_resident, avg[0], avg[1], avg[2], avg[3], avg[4], avg[5], avg[6],
+                avg[7], avg[8], avg[9]);
+    }
     return 0;
 }
 
@@ -612,6 +701,7 @@ extern "C" int amc3d_fused_sa_forward(int b, int n, int m, int c, int o, int nsa
     AMC3D_REQUIRE(nsample == 16 || nsample == 32, AMC3D_ELIMIT, "fused_sa_forward: nsample=%d (16 and 32 are built)", nsample);
     AMC3D_REQUIRE(precision == 1 || precision == 3, AMC3D_EINVAL, "fused_sa_forward: precision=%d is not 1 (TF32) / 3 (3xTF32)", precision);
     AMC3D_REQUIRE(b <= 65535 && (long long)b * m < (1ll << 31) / 64, AMC3D_ELIMIT, "fused_sa_forward: batch %d x %d queries too large", b, m);
+    AMC3D_REQUIRE((long long)b * n * c < (1ll << 31), AMC3D_ELIMIT, "fused_sa_forward: %d x %d x %d features exceed 2^31 elements", b, n, c);
     if (b == 0 || m == 0) return 0;
     cudaStream_t st = as_stream(stream);
     FusedFwdArgs a;

@@ -445,22 +445,22 @@ def time_fused_operator(replay, dev, iters=3):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / iters
 
-    def timed_graph(fn):
-        """the same forward + backward pass recorded into ONE CUDA graph and replayed: what the pass costs once
-        per-call Python and launch latency are out of the picture (None if the pass cannot be captured)"""
+    def timed_graph(fn, backward=True):
+        """the same pass recorded into ONE CUDA graph and replayed: what it costs on the GPU once per-call Python
+        and launch latency are out of the picture (a string with the reason if the pass cannot be captured)"""
         try:
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
                 for _ in range(2):
-                    fn(True)
+                    fn(backward)
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize()
             for w in work:
                 w[5].grad = None
             g_ = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g_):
-                fn(True)
+                fn(backward)
             for _ in range(2):
                 g_.replay()
             torch.cuda.synchronize()
@@ -483,22 +483,30 @@ def time_fused_operator(replay, dev, iters=3):
         c_fwd, c_all = timed(composed_pass, False), timed(composed_pass, True)
         f_graph = timed_graph(fused_pass)
         c_graph = timed_graph(composed_pass)
+        f_fgraph = timed_graph(fused_pass, False)
+        c_fgraph = timed_graph(composed_pass, False)
+        gpu_fwd = f_fgraph if isinstance(f_fgraph, float) else f_fwd   # GPU time of the forward (eager if not captured)
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-        tf32_peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
+        tf32_peak = float(peaks.get("bf16_tflops", 1660.0)) / 2.0       # the forward is ~2 ms of tensor work: burst figure
         res = {"layers": len(work), "conv_gflop_fwd": round(flop / 1e9, 1),
-               "fused": {"fwd_ms": round(f_fwd, 3), "fwd_bwd_ms": round(f_all, 3), "fwd_bwd_graph_ms": f_graph},
-               "composition": {"fwd_ms": round(c_fwd, 3), "fwd_bwd_ms": round(c_all, 3), "fwd_bwd_graph_ms": c_graph,
+               "fused": {"fwd_ms": round(f_fwd, 3), "fwd_bwd_ms": round(f_all, 3), "fwd_graph_ms": f_fgraph,
+                         "fwd_bwd_graph_ms": f_graph},
+               "composition": {"fwd_ms": round(c_fwd, 3), "fwd_bwd_ms": round(c_all, 3), "fwd_graph_ms": c_fgraph,
+                               "fwd_bwd_graph_ms": c_graph,
                                "what": "QueryAndGroup (this package's grouping kernels) + cat + cuDNN Conv2d 1x1 (TF32) + "
                                        "BatchNorm2d (training) + ReLU + max, torch autograd"},
                "speedup_fwd": round(c_fwd / f_fwd, 2), "speedup_fwd_bwd": round(c_all / f_all, 2),
                "speedup_fwd_bwd_graph": (round(c_graph / f_graph, 2) if isinstance(f_graph, float) and isinstance(c_graph, float)
                                          else None),
-               "fused_fwd_tflops": round(flop / (f_fwd * 1e-3) / 1e12, 1),
-               "tensor_roofline": {"bound": "tensor", "achieved": round(flop / (f_fwd * 1e-3) / 1e12, 1), "peak": tf32_peak,
-                                   "unit": "TFLOP/s", "frac": round(flop / (f_fwd * 1e-3) / 1e12 / tf32_peak, 4),
-                                   "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 runs at half the bf16 rate)",
-                                   "note": "forward only, eager, whole operator (transpose, weight packing, statistics, normalise "
-                                           "included); the backward does 1/16 of these FLOPs by construction"},
+               "speedup_fwd_graph": (round(c_fgraph / f_fgraph, 2) if isinstance(f_fgraph, float) and isinstance(c_fgraph, float)
+                                     else None),
+               "fused_fwd_tflops": round(flop / (gpu_fwd * 1e-3) / 1e12, 1),
+               "tensor_roofline": {"bound": "tensor", "achieved": round(flop / (gpu_fwd * 1e-3) / 1e12, 1), "peak": tf32_peak,
+                                   "unit": "TFLOP/s", "frac": round(flop / (gpu_fwd * 1e-3) / 1e12 / tf32_peak, 4),
+                                   "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst, cuBLAS) / 2: TF32 runs at half the bf16 rate",
+                                   "note": "forward of the 19 layers as one CUDA graph = GPU time of the whole operator (transpose, "
+                                           "weight tiles, the tcgen05 kernel, statistics, normalise); the tcgen05 kernel alone: "
+                                           "profiles/r02_fused.md; the backward does 1/16 of these FLOPs by construction"},
                "grouped_tensor_bytes_avoided_fwd": int(sum(4.0 * replay.B * w[0].shape[1] * 32 * (w[5].shape[1] + 3) for w in work)),
                "mode": "eager (per-call Python included on both sides), TF32 operands on both sides, 3 iterations after 2 warm-ups"}
     except Exception as e:                                     # never break the headline line

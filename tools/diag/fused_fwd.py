@@ -20,9 +20,9 @@ def ref(q, p, f, idx, w, gamma, beta, radius, eps=1e-5):
 cases = [(2, 600, 600, 32, 32, 16, 0.2), (2, 400, 400, 64, 64, 32, 0.25), (2, 800, 200, 32, 64, 16, 0.15),
          (2, 2048, 2048, 128, 128, 32, 0.2), (8, 6000, 6000, 128, 128, 32, 0.2), (8, 24000, 6000, 64, 128, 32, 0.1),
          (8, 1500, 1500, 256, 256, 32, 0.4), (8, 375, 375, 512, 512, 32, 0.8), (8, 93, 93, 1024, 1024, 32, 1.6)]
-only = int(sys.argv[1]) if len(sys.argv) > 1 else None
+only = [int(x) for x in sys.argv[1].split(',')] if len(sys.argv) > 1 else None
 for ci, (B, N, M, C, O, ns, radius) in enumerate(cases):
-    if only is not None and ci != only: continue
+    if only is not None and ci not in only: continue
     xyz, _ = scenes.batch_of_scenes(B, N, "surface", first_scene=31)
     p = torch.from_numpy(xyz).cuda()
     if M == N: q = p
