@@ -752,7 +752,7 @@ fused_sa_bwd_scatter_kernel(int B, int N, int M, int O, int NS, float inv_radius
                             const unsigned char *__restrict__ arg, const int *__restrict__ idx,
                             const float *__restrict__ xyz, const float *__restrict__ qxyz,
                             const float *__restrict__ mean, const float *__restrict__ invstd,
-                            const float *__restrict__ gamma, float *__restrict__ A, double *__restrict__ dbeta,
+                            const float *__restrict__ gamma, float *__restrict__ A, int lda, double *__restrict__ dbeta,
                             double *__restrict__ dgamma, double *__restrict__ wdp) {
     __shared__ float t[32][33];
     __shared__ float red[5][8][32];
@@ -786,7 +786,7 @@ fused_sa_bwd_scatter_kernel(int B, int N, int M, int O, int NS, float inv_radius
                     const int s = __ldg(arg + q * O + o);
                     const long long row = (long long)b * N + __ldg(idx + q * NS + s);
                     const float gg = g * gh;
-                    atomicAdd(A + row * O + o, gg);
+                    atomicAdd(A + row * lda + o, gg);
 #pragma unroll
                     for (int j = 0; j < 3; ++j)
                         sd[j] += gg * ((__ldg(xyz + row * 3 + j) - __ldg(qxyz + q * 3 + j)) * inv_radius);
@@ -812,8 +812,8 @@ fused_sa_bwd_scatter_kernel(int B, int N, int M, int O, int NS, float inv_radius
 // coordinates; mom[0..2] = sum_p dp, mom[3..11] = sum_p dp dp^T  (f64)
 __global__ void __launch_bounds__(256)
 fused_sa_moments_kernel(int B, int N, int M, int NS, float inv_radius, const float *__restrict__ xyz,
-                        const float *__restrict__ qxyz, const int *__restrict__ idx, float *__restrict__ cnt,
-                        float *__restrict__ dpsum, double *__restrict__ mom) {
+                        const float *__restrict__ qxyz, const int *__restrict__ idx, float *__restrict__ cnt, int ldc,
+                        float *__restrict__ dpsum, int ldd, double *__restrict__ mom) {
     const long long P = (long long)B * M * NS;
     const long long p = (long long)blockIdx.x * 256 + threadIdx.x;
     float d[3] = {0.f, 0.f, 0.f};
@@ -823,9 +823,9 @@ fused_sa_moments_kernel(int B, int N, int M, int NS, float inv_radius, const flo
         const long long row = b * N + __ldg(idx + p);
 #pragma unroll
         for (int j = 0; j < 3; ++j) d[j] = (__ldg(xyz + row * 3 + j) - __ldg(qxyz + q * 3 + j)) * inv_radius;
-        atomicAdd(cnt + row, 1.f);
+        atomicAdd(cnt + row * ldc, 1.f);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) atomicAdd(dpsum + row * 3 + j, d[j]);
+        for (int j = 0; j < 3; ++j) atomicAdd(dpsum + row * ldd + j, d[j]);
     }
     float v[12] = {d[0], d[1], d[2], d[0] * d[0], d[0] * d[1], d[0] * d[2], d[1] * d[0], d[1] * d[1], d[1] * d[2],
                    d[2] * d[0], d[2] * d[1], d[2] * d[2]};
@@ -844,38 +844,76 @@ fused_sa_moments_kernel(int B, int N, int M, int NS, float inv_radius, const flo
     }
 }
 
+// zero `ncols` floats at the start of each of `rows` rows that are `ld` floats apart (a 2-D memset of narrow rows
+// is far slower than this)
+__global__ void __launch_bounds__(256)
+fused_sa_zero_cols_kernel(float *__restrict__ base, long long rows, int ld, int ncols) {
+    const long long total = rows * ncols;
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        const long long r = e / ncols;
+        base[r * ld + (e - r * ncols)] = 0.f;
+    }
+}
+__global__ void __launch_bounds__(256)
+fused_sa_zero_cols4_kernel(float4 *__restrict__ base, long long rows, int ld4, int ncols4) {
+    const long long total = rows * ncols4;
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        const long long r = e / ncols4;
+        base[r * ld4 + (e - r * ncols4)] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+static void zero_cols(float *base, long long rows, int ld, int ncols, cudaStream_t st) {
+    if (rows <= 0 || ncols <= 0) return;
+    if (ld == ncols) {
+        cudaMemsetAsync(base, 0, sizeof(float) * (size_t)rows * ncols, st);
+    } else if (ld % 4 == 0 && ncols % 4 == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0) {
+        const long long total = rows * (ncols / 4);
+        fused_sa_zero_cols4_kernel<<<(unsigned)min(div_up_ll(total, 256), (long long)kNumSMs * 16), 256, 0, st>>>(
+            reinterpret_cast<float4 *>(base), rows, ld / 4, ncols / 4);
+    } else {
+        const long long total = rows * ncols;
+        fused_sa_zero_cols_kernel<<<(unsigned)min(div_up_ll(total, 256), (long long)kNumSMs * 16), 256, 0, st>>>(base, rows, ld, ncols);
+    }
+}
+
 }  // namespace amc3d
 
 extern "C" int amc3d_fused_sa_backward_scatter(int b, int n, int m, int o, int nsample, float radius, int normalize_dp,
                                                const float *grad_out, const float *out, const float *ysel,
                                                const unsigned char *arg, const int *idx, const float *xyz,
                                                const float *new_xyz, const float *mean, const float *invstd,
-                                               const float *gamma, float *a_scatter, double *dbeta_dgamma_wdp,
+                                               const float *gamma, float *a_scatter, int lda, double *dbeta_dgamma_wdp,
                                                void *stream) {
     AMC3D_REQUIRE(b >= 0 && n >= 1 && m >= 0 && o >= 1 && nsample >= 1, AMC3D_EINVAL, "fused_sa_backward_scatter: bad sizes");
     AMC3D_REQUIRE(b <= 65535, AMC3D_ELIMIT, "fused_sa_backward_scatter: batch %d > 65535", b);
+    AMC3D_REQUIRE(lda >= o, AMC3D_EINVAL, "fused_sa_backward_scatter: row stride %d < O = %d", lda, o);
     cudaStream_t st = as_stream(stream);
     cudaMemsetAsync(dbeta_dgamma_wdp, 0, sizeof(double) * 5 * (size_t)o, st);
-    cudaMemsetAsync(a_scatter, 0, sizeof(float) * (size_t)b * n * o, st);
+    zero_cols(a_scatter, (long long)b * n, lda, o, st);
     if (b == 0 || m == 0) return check_launch("fused_sa_backward_scatter");
     dim3 grid(div_up(m, 32), div_up(o, 32), b);
     fused_sa_bwd_scatter_kernel<<<grid, 256, 0, st>>>(b, n, m, o, nsample, normalize_dp ? 1.0f / radius : 1.0f, grad_out, out,
-                                                      ysel, arg, idx, xyz, new_xyz, mean, invstd, gamma, a_scatter,
+                                                      ysel, arg, idx, xyz, new_xyz, mean, invstd, gamma, a_scatter, lda,
                                                       dbeta_dgamma_wdp, dbeta_dgamma_wdp + o, dbeta_dgamma_wdp + 2 * o);
     return check_launch("fused_sa_backward_scatter");
 }
 
 extern "C" int amc3d_fused_sa_moments(int b, int n, int m, int nsample, float radius, int normalize_dp,
-                                      const float *xyz, const float *new_xyz, const int *idx, float *cnt,
-                                      float *dpsum, double *mom, void *stream) {
+                                      const float *xyz, const float *new_xyz, const int *idx, float *cnt, int ld_cnt,
+                                      float *dpsum, int ld_dps, double *mom, void *stream) {
     AMC3D_REQUIRE(b >= 0 && n >= 1 && m >= 0 && nsample >= 1, AMC3D_EINVAL, "fused_sa_moments: bad sizes");
+    AMC3D_REQUIRE(ld_cnt >= 1 && ld_dps >= 3, AMC3D_EINVAL, "fused_sa_moments: row strides %d, %d", ld_cnt, ld_dps);
     cudaStream_t st = as_stream(stream);
-    cudaMemsetAsync(cnt, 0, sizeof(float) * (size_t)b * n, st);
-    cudaMemsetAsync(dpsum, 0, sizeof(float) * 3 * (size_t)b * n, st);
+    if (dpsum + 3 == cnt && ld_cnt == ld_dps) {                     // [dpsum | cnt] side by side: one pass
+        zero_cols(dpsum, (long long)b * n, ld_dps, 4, st);
+    } else {
+        zero_cols(cnt, (long long)b * n, ld_cnt, 1, st);
+        zero_cols(dpsum, (long long)b * n, ld_dps, 3, st);
+    }
     cudaMemsetAsync(mom, 0, sizeof(double) * 12, st);
     const long long P = (long long)b * m * nsample;
     if (P > 0)
         fused_sa_moments_kernel<<<(unsigned)div_up_ll(P, 256), 256, 0, st>>>(b, n, m, nsample, normalize_dp ? 1.0f / radius : 1.0f,
-                                                                              xyz, new_xyz, idx, cnt, dpsum, mom);
+                                                                              xyz, new_xyz, idx, cnt, ld_cnt, dpsum, ld_dps, mom);
     return check_launch("fused_sa_moments");
 }

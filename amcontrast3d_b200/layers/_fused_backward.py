@@ -15,7 +15,11 @@ the conv output is
   cnt[n] = #{p: idx[p] = n}  (amc3d_fused_sa_moments):   sum_p f f^T = sum_n cnt[n] f[n] f[n]^T :
       dW'  -=  c0 (x) Sx  +  diag(c1) W' Sxx
       df[n] -=  cnt[n] v_f  +  Q_ff (cnt[n] f[n])  +  Q_fd dpsum[n],      Q = W'^T diag(c1) W',  v = W'^T c0
-All products here are plain library GEMMs (torch.matmul), none larger than (B*N) x O x C.  W' is the conv weight in
+All products here are plain library GEMMs (torch.matmul).  The per-support-point quantities are kept as the column
+blocks of ONE matrix  X = [A | cnt*f | dpsum | cnt]  of shape (B*N, O+C+4) that the two kernels fill in place, so that
+    f^T X  = [ (A^T f)^T | sum_n cnt f f^T | sum_p f dp^T | sum_n cnt f ]     (every moment dW needs, one GEMM)
+    df     = X [ W_f ; -Q_ff^T ; -Q_fd^T ; -v_f^T ]                             (one GEMM)
+instead of eight products and their read-modify-write accumulations over (B*N)-row arrays.  W' is the conv weight in
 the packed column order [features | dp] of fused.pack_weight.
 """
 from __future__ import annotations
@@ -24,6 +28,17 @@ import torch
 
 from .. import _capi
 from .._capi import ptr, stream
+
+
+def _tall_tn(a, b, B, N):
+    """a^T b for two tall matrices with B*N rows: split the long reduction into row blocks (batched GEMM + a sum of the
+    partial products) — the library's single-GEMM heuristics launch a handful of CTAs for a (C x B*N) @ (B*N x K) product"""
+    s = next((d for d in (16, 12, 10, 8, 6, 5, 4, 3, 2) if N % d == 0 and N // d >= 1024), 1)
+    nb = B * s
+    if nb == 1:
+        return a.t() @ b
+    part = torch.bmm(a.view(nb, -1, a.shape[1]).transpose(1, 2), b.view(nb, -1, b.shape[1]))
+    return part.sum(0)
 
 
 def backward(ctx, grad_out):
@@ -36,17 +51,19 @@ def backward(ctx, grad_out):
     P = float(B * M * ns)
     dev = fT.device
     G = grad_out.contiguous().float()
-    A = torch.empty((B * N, O), dtype=torch.float32, device=dev)
+    # ONE (B*N, O + C + 4) matrix  X = [ A | cnt * f | dpsum | cnt ]: the kernels write their column blocks in place
+    # (row stride Kc), so that the feature gradient is one GEMM with it and every weight-gradient moment another
+    Kc = O + C + 4
+    X = torch.empty((B * N, Kc), dtype=torch.float32, device=dev)
+    A, Fw, dps, cnt = X[:, :O], X[:, O:O + C], X[:, O + C:O + C + 3], X[:, O + C + 3:]
     red = torch.empty((5 * O,), dtype=torch.float64, device=dev)
-    cnt = torch.empty((B * N, 1), dtype=torch.float32, device=dev)
-    dps = torch.empty((B * N, 3), dtype=torch.float32, device=dev)
     mom = torch.empty((12,), dtype=torch.float64, device=dev)
     with _capi.guard(fT):
         st = stream(fT)
         _capi.call("amc3d_fused_sa_backward_scatter", B, N, M, O, ns, radius, int(normalize_dp), ptr(G), ptr(out),
-                   ptr(ysel), ptr(arg), ptr(idx), ptr(p), ptr(q), ptr(mean), ptr(invstd), ptr(gamma), ptr(A), ptr(red), st)
-        _capi.call("amc3d_fused_sa_moments", B, N, M, ns, radius, int(normalize_dp), ptr(p), ptr(q), ptr(idx), ptr(cnt),
-                   ptr(dps), ptr(mom), st)
+                   ptr(ysel), ptr(arg), ptr(idx), ptr(p), ptr(q), ptr(mean), ptr(invstd), ptr(gamma), ptr(A), Kc, ptr(red), st)
+        _capi.call("amc3d_fused_sa_moments", B, N, M, ns, radius, int(normalize_dp), ptr(p), ptr(q), ptr(idx), ptr(cnt), Kc,
+                   ptr(dps), Kc, ptr(mom), st)
     dbeta, dgamma, wdp = red[:O], red[O:2 * O], red[2 * O:].view(O, 3)
     # O-sized coefficient vectors in FP64; the GEMMs in FP32 (TF32 tensor cores in 'tf32' mode, as the reference's
     # cuDNN backward would use; exact FP32 in the FP32-faithful mode)
@@ -59,22 +76,21 @@ def backward(ctx, grad_out):
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = precision == "tf32"
     try:
-        Fw = f2 * cnt                                        # cnt[n] f[n]
-        Sff = f2.t() @ Fw                                    # sum_n cnt f f^T       (C, C)
-        Sfd = f2.t() @ dps                                   # sum_p f dp^T          (C, 3)
+        torch.mul(f2, cnt, out=Fw)                           # cnt[n] f[n]
+        G1 = _tall_tn(f2, X, B, N)                           # (C, Kc) = [ (A^T f)^T | sum cnt f f^T | sum_p f dp^T | sum cnt f ]
+        Sff, Sfd = G1[:, O:O + C], G1[:, O + C:O + C + 3]
         Sdd = mom[3:12].view(3, 3).float()
         Sxx = torch.cat([torch.cat([Sff, Sfd], 1), torch.cat([Sfd.t(), Sdd], 1)], 0)      # (Kq, Kq)
-        Sx = torch.cat([Fw.sum(0), mom[0:3].float()])
+        Sx = torch.cat([G1[:, O + C + 3], mom[0:3].float()])
         c1W = c1[:, None] * W
         Qm = W.t() @ c1W                                     # W'^T diag(c1) W'      (Kq, Kq)
-        v = (W.t() @ c0[:, None]).t()                        # (1, Kq)
-        dWp = torch.cat([A.t() @ f2, wdp.float()], 1)        # the arg-max term
+        v = W.t() @ c0[:, None]                              # (Kq, 1)
+        dWp = torch.cat([G1[:, :O].t(), wdp.float()], 1)     # the arg-max term
         dWp.addmm_(c0[:, None], Sx[None, :], alpha=-1.0)
         dWp.addmm_(c1W, Sxx, alpha=-1.0)
-        dfT = A @ W[:, :C]                                   # the arg-max term       (B*N, C)
-        dfT.addmm_(cnt, v[:, :C], alpha=-1.0)
-        dfT.addmm_(Fw, Qm[:C, :C].t(), alpha=-1.0)
-        dfT.addmm_(dps, Qm[:C, C:].t(), alpha=-1.0)
+        # df[n] = A[n] W_f - Q_ff (cnt f)[n] - Q_fd dpsum[n] - cnt[n] v_f   as one product  X @ Wc
+        Wc = torch.cat([W[:, :C], -Qm[:C, :C].t(), -Qm[:C, C:].t(), -v[:C].t()], 0)       # (Kc, C)
+        dfT = X @ Wc                                         # (B*N, C)
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
     dW = torch.cat([dWp[:, C:], dWp[:, :C]], 1).reshape(wshape)

@@ -185,22 +185,25 @@ int amc3d_fused_sa_forward(int b, int n, int m, int c, int o, int nsample, float
 /* Backward of amc3d_fused_sa_forward: two device steps around a few small library GEMMs on the host side
  * (amcontrast3d_b200/layers/_fused_backward.py has the algebra; csrc/fused_sa.cu the derivation).
  *  _backward_scatter  G' = grad_out * [out > 0]; dbeta_dgamma_wdp (5*O) f64 = [sum G' | sum G' yhat | dW of the
- *                     three relative-coordinate columns (O,3)]; and a_scatter (B*N, O) f32:
- *                     A[n,o] = sum over the queries whose arg-max sample of channel o is support point n of
- *                     gamma_o invstd_o G'[q,o].  Then dW_f = A^T f and df = A W_f are (B*N) x O x C GEMMs,
- *                     1/nsample of the convolution's work.  Zeroes its outputs itself.
- *  _moments           per support point cnt (B,N) f32 and dpsum (B,N,3) f32 (how often / with which relative
- *                     coordinates it is grouped) and mom (12) f64 = [sum dp (3) | sum dp dp^T (9)]: with these
- *                     the dense BatchNorm terms of the gradient reduce to (B*N) x C x C GEMMs. */
+ *                     three relative-coordinate columns (O,3)]; and a_scatter (B*N rows of O floats, `lda`
+ *                     floats apart): A[n,o] = sum over the queries whose arg-max sample of channel o is
+ *                     support point n of gamma_o invstd_o G'[q,o].  Then dW_f = A^T f and df = A W_f are
+ *                     (B*N) x O x C GEMMs, 1/nsample of the convolution's work.  Zeroes its outputs itself.
+ *  _moments           per support point cnt (B*N rows, ld_cnt floats apart) and dpsum (B*N rows of 3 floats,
+ *                     ld_dps apart) (how often / with which relative coordinates it is grouped) and mom (12) f64 =
+ *                     [sum dp (3) | sum dp dp^T (9)]: with these the dense BatchNorm terms of the gradient
+ *                     reduce to (B*N) x C x C GEMMs.
+ * The row strides let the host keep A, cnt * f, dpsum and cnt as column blocks of ONE (B*N, O+C+4) matrix, so that
+ * the whole feature gradient is one GEMM with it and all weight-gradient moments another. */
 int amc3d_fused_sa_backward_scatter(int b, int n, int m, int o, int nsample, float radius, int normalize_dp,
                                     const float *grad_out, const float *out, const float *ysel,
                                     const unsigned char *arg, const int *idx, const float *xyz,
                                     const float *new_xyz, const float *mean, const float *invstd,
-                                    const float *gamma, float *a_scatter, double *dbeta_dgamma_wdp,
+                                    const float *gamma, float *a_scatter, int lda, double *dbeta_dgamma_wdp,
                                     void *stream);
 int amc3d_fused_sa_moments(int b, int n, int m, int nsample, float radius, int normalize_dp,
-                           const float *xyz, const float *new_xyz, const int *idx, float *cnt,
-                           float *dpsum, double *mom, void *stream);
+                           const float *xyz, const float *new_xyz, const int *idx, float *cnt, int ld_cnt,
+                           float *dpsum, int ld_dps, double *mom, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * Input side: voxel hash and crop distances of the dataset code
