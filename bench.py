@@ -504,6 +504,7 @@ def time_fused_operator(replay, dev, iters=3):
                "tensor_roofline": {"bound": "tensor", "achieved": round(flop / (gpu_fwd * 1e-3) / 1e12, 1), "peak": tf32_peak,
                                    "unit": "TFLOP/s", "frac": round(flop / (gpu_fwd * 1e-3) / 1e12 / tf32_peak, 4),
                                    "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst, cuBLAS) / 2: TF32 runs at half the bf16 rate",
+                                   "peak_nominal": 1125.0, "frac_nominal": round(flop / (gpu_fwd * 1e-3) / 1e12 / 1125.0, 4),
                                    "note": "forward of the 19 layers as one CUDA graph = GPU time of the whole operator (transpose, "
                                            "weight tiles, the tcgen05 kernel, statistics, normalise); the tcgen05 kernel alone: "
                                            "profiles/r02_fused.md; the backward does 1/16 of these FLOPs by construction"},
