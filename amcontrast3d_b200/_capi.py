@@ -59,6 +59,8 @@ SIGNATURES = {
     "amc3d_fused_sa_forward": [_I, _I, _I, _I, _I, _I, _F, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                _P, _P, _P, _P],
     "amc3d_fused_sa_backward_scatter": [_I, _I, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P],
+    "amc3d_fused_sa_backward_coefs": [_I, _I, ctypes.c_double, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "amc3d_fused_sa_backward_assemble": [_I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "amc3d_fused_sa_moments": [_I, _I, _I, _I, _F, _I, _P, _P, _P, _P, _I, _P, _I, _P, _P],
     "amc3d_voxel_keys": [_LL, ctypes.c_double, _P, _P, _P, _P],
     "amc3d_crop_dist2": [_LL, _P, _LL, _P, _P],

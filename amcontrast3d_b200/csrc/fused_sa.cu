@@ -844,6 +844,73 @@ fused_sa_moments_kernel(int B, int N, int M, int NS, float inv_radius, const flo
     }
 }
 
+// O-sized coefficient vectors of the dense BatchNorm terms, in FP64 from the FP64 sums:
+//   ghat = gamma invstd,  c1 = ghat invstd dgamma / P,  c0 = ghat dbeta / P - c1 mean
+// and the row-scaled weights: c1wx (O, Kp) = [ c1 (.) W' | c0 | 0 ]  (one GEMM with W'^T then gives both Q = W'^T diag(c1) W'
+// and v = W'^T c0; Kp = C + 8 columns like W' itself, so that every GEMM dimension is a multiple of 8 and the library
+// stays on its tensor-core kernels).  Also the FP32 copies of dgamma / dbeta the caller returns.
+__global__ void __launch_bounds__(128)
+fused_sa_bwd_coef_kernel(int O, int Kq, int Kp, double P, const float *__restrict__ gamma, const float *__restrict__ invstd,
+                         const float *__restrict__ mean, const double *__restrict__ red, const float *__restrict__ Wp,
+                         float *__restrict__ c1wx, float *__restrict__ dgamma_f, float *__restrict__ dbeta_f) {
+    const int o = blockIdx.x;
+    const double is = (double)__ldg(invstd + o), ghat = (double)__ldg(gamma + o) * is;
+    const double c1d = ghat * is * red[O + o] / P;
+    const double c0d = ghat * red[o] / P - c1d * (double)__ldg(mean + o);
+    const float c1f = (float)c1d;
+    float *row = c1wx + (size_t)o * Kp;
+    for (int k = threadIdx.x; k < Kp; k += 128) row[k] = k < Kq ? c1f * __ldg(Wp + (size_t)o * Kp + k) : 0.f;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        row[Kq] = (float)c0d;
+        dgamma_f[o] = (float)red[O + o];
+        dbeta_f[o] = (float)red[o];
+    }
+}
+
+// the small matrices of the backward in one pass (Kq = C + 3, Kp = C + 8, Kc = O + C + 4; g1 = f^T X is (C, Kc),
+// qv = W'^T c1wx is (Kp, Kp) with [Q | v] in its first Kq rows and Kq + 1 columns; outputs padded to Kp with zeros):
+//   sxx (Kp, Kp) = [[S_ff, S_fd], [S_fd^T, S_dd]]                       second moments of the grouped input
+//   wc  (Kc, C)  = [ W_f ; -Q_ff^T ; -Q_fd^T ; -v_f^T ]                  df = X wc
+//   dwp (O, Kp)  = [ (A^T f) | wdp ] - c0 (x) S_x                        the arg-max term and the c0 term of dW'
+__global__ void __launch_bounds__(256)
+fused_sa_bwd_assemble_kernel(int O, int C, const float *__restrict__ g1, const double *__restrict__ mom,
+                             const double *__restrict__ wdp, const float *__restrict__ Wp, const float *__restrict__ qv,
+                             const float *__restrict__ c1wx, float *__restrict__ sxx, float *__restrict__ wc,
+                             float *__restrict__ dwp) {
+    const int Kq = C + 3, Kp = C + 8, Kc = O + C + 4;
+    const long long n1 = (long long)Kp * Kp, n2 = (long long)Kc * C, n3 = (long long)O * Kp;
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < n1 + n2 + n3; e += (long long)gridDim.x * 256) {
+        if (e < n1) {
+            const int i = (int)(e / Kp), j = (int)(e - (long long)i * Kp);
+            float x = 0.f;
+            if (i < Kq && j < Kq) {
+                if (i < C) x = g1[(size_t)i * Kc + O + j];                        // S_ff | S_fd (columns O + C + (j - C))
+                else if (j < C) x = g1[(size_t)j * Kc + O + i];                   // S_fd^T
+                else x = (float)mom[3 + (i - C) * 3 + (j - C)];
+            }
+            sxx[e] = x;
+        } else if (e < n1 + n2) {
+            const long long t = e - n1;
+            const int r = (int)(t / C), c = (int)(t - (long long)r * C);
+            float x;
+            if (r < O) x = __ldg(Wp + (size_t)r * Kp + c);
+            else x = -qv[(size_t)c * Kp + (r - O)];                               // -Q[c, j] for j < Kq, then -v[c] (column Kq)
+            wc[t] = x;
+        } else {
+            const long long t = e - n1 - n2;
+            const int o = (int)(t / Kp), k = (int)(t - (long long)o * Kp);
+            float x = 0.f;
+            if (k < Kq) {
+                const float base = k < C ? g1[(size_t)k * Kc + o] : (float)wdp[o * 3 + (k - C)];
+                const float sx = k < C ? g1[(size_t)k * Kc + O + C + 3] : (float)mom[k - C];
+                x = base - c1wx[(size_t)o * Kp + Kq] * sx;
+            }
+            dwp[t] = x;
+        }
+    }
+}
+
 // zero `ncols` floats at the start of each of `rows` rows that are `ld` floats apart (a 2-D memset of narrow rows
 // is far slower than this)
 __global__ void __launch_bounds__(256)
@@ -916,4 +983,23 @@ extern "C" int amc3d_fused_sa_moments(int b, int n, int m, int nsample, float ra
         fused_sa_moments_kernel<<<(unsigned)div_up_ll(P, 256), 256, 0, st>>>(b, n, m, nsample, normalize_dp ? 1.0f / radius : 1.0f,
                                                                               xyz, new_xyz, idx, cnt, ld_cnt, dpsum, ld_dps, mom);
     return check_launch("fused_sa_moments");
+}
+
+extern "C" int amc3d_fused_sa_backward_coefs(int c, int o, double positions, const float *gamma, const float *invstd,
+                                             const float *mean, const double *dbeta_dgamma_wdp, const float *w_packed,
+                                             float *c1wx, float *dgamma, float *dbeta, void *stream) {
+    AMC3D_REQUIRE(c >= 1 && o >= 1 && positions > 0, AMC3D_EINVAL, "fused_sa_backward_coefs: bad sizes");
+    fused_sa_bwd_coef_kernel<<<o, 128, 0, as_stream(stream)>>>(o, c + 3, c + 8, positions, gamma, invstd, mean, dbeta_dgamma_wdp,
+                                                               w_packed, c1wx, dgamma, dbeta);
+    return check_launch("fused_sa_backward_coefs");
+}
+
+extern "C" int amc3d_fused_sa_backward_assemble(int c, int o, const float *g1, const double *mom,
+                                                const double *dbeta_dgamma_wdp, const float *w_packed, const float *qv,
+                                                const float *c1wx, float *sxx, float *wc, float *dwp, void *stream) {
+    AMC3D_REQUIRE(c >= 1 && o >= 1, AMC3D_EINVAL, "fused_sa_backward_assemble: bad sizes");
+    const long long total = (long long)(c + 8) * (c + 8) + (long long)(o + c + 4) * c + (long long)o * (c + 8);
+    fused_sa_bwd_assemble_kernel<<<(unsigned)min(div_up_ll(total, 256), (long long)kNumSMs * 8), 256, 0, as_stream(stream)>>>(
+        o, c, g1, mom, dbeta_dgamma_wdp + 2 * (size_t)o, w_packed, qv, c1wx, sxx, wc, dwp);
+    return check_launch("fused_sa_backward_assemble");
 }

@@ -64,37 +64,34 @@ def backward(ctx, grad_out):
                    ptr(ysel), ptr(arg), ptr(idx), ptr(p), ptr(q), ptr(mean), ptr(invstd), ptr(gamma), ptr(A), Kc, ptr(red), st)
         _capi.call("amc3d_fused_sa_moments", B, N, M, ns, radius, int(normalize_dp), ptr(p), ptr(q), ptr(idx), ptr(cnt), Kc,
                    ptr(dps), Kc, ptr(mom), st)
-    dbeta, dgamma, wdp = red[:O], red[O:2 * O], red[2 * O:].view(O, 3)
-    # O-sized coefficient vectors in FP64; the GEMMs in FP32 (TF32 tensor cores in 'tf32' mode, as the reference's
-    # cuDNN backward would use; exact FP32 in the FP32-faithful mode)
-    ghat = gamma.double() * invstd.double()
-    c1d = ghat * invstd.double() * dgamma / P
-    c0 = (ghat * dbeta / P - c1d * mean.double()).float()
-    c1 = c1d.float()
-    W = wp[:, :Kq]                                           # (O, Kq) packed [f | dp]
+    # O-sized coefficient vectors in FP64 (amc3d_fused_sa_backward_coefs); the GEMMs in FP32 (TF32 tensor cores in
+    # 'tf32' mode, as the reference's cuDNN backward would use; exact FP32 in the FP32-faithful mode)
     f2 = fT.view(B * N, C)
+    Kp = wp.shape[1]                                         # C + 8: small matrices padded like W' (GEMM dims % 8 == 0)
+    c1wx = torch.empty((O, Kp), dtype=torch.float32, device=dev)              # [ c1 (.) W' | c0 | 0 ]
+    dgamma = torch.empty((O,), dtype=torch.float32, device=dev)
+    dbeta = torch.empty((O,), dtype=torch.float32, device=dev)
+    sxx = torch.empty((Kp, Kp), dtype=torch.float32, device=dev)
+    wc = torch.empty((Kc, C), dtype=torch.float32, device=dev)
+    dWp = torch.empty((O, Kp), dtype=torch.float32, device=dev)
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = precision == "tf32"
     try:
+        with _capi.guard(fT):
+            _capi.call("amc3d_fused_sa_backward_coefs", C, O, P, ptr(gamma), ptr(invstd), ptr(mean), ptr(red), ptr(wp),
+                       ptr(c1wx), ptr(dgamma), ptr(dbeta), st)
         torch.mul(f2, cnt, out=Fw)                           # cnt[n] f[n]
         G1 = _tall_tn(f2, X, B, N)                           # (C, Kc) = [ (A^T f)^T | sum cnt f f^T | sum_p f dp^T | sum cnt f ]
-        Sff, Sfd = G1[:, O:O + C], G1[:, O + C:O + C + 3]
-        Sdd = mom[3:12].view(3, 3).float()
-        Sxx = torch.cat([torch.cat([Sff, Sfd], 1), torch.cat([Sfd.t(), Sdd], 1)], 0)      # (Kq, Kq)
-        Sx = torch.cat([G1[:, O + C + 3], mom[0:3].float()])
-        c1W = c1[:, None] * W
-        Qm = W.t() @ c1W                                     # W'^T diag(c1) W'      (Kq, Kq)
-        v = W.t() @ c0[:, None]                              # (Kq, 1)
-        dWp = torch.cat([G1[:, :O].t(), wdp.float()], 1)     # the arg-max term
-        dWp.addmm_(c0[:, None], Sx[None, :], alpha=-1.0)
-        dWp.addmm_(c1W, Sxx, alpha=-1.0)
-        # df[n] = A[n] W_f - Q_ff (cnt f)[n] - Q_fd dpsum[n] - cnt[n] v_f   as one product  X @ Wc
-        Wc = torch.cat([W[:, :C], -Qm[:C, :C].t(), -Qm[:C, C:].t(), -v[:C].t()], 0)       # (Kc, C)
-        dfT = X @ Wc                                         # (B*N, C)
+        QV = wp.t() @ c1wx                                   # (Kp, Kp) = [ W'^T diag(c1) W' | W'^T c0 | 0 ]
+        with _capi.guard(fT):
+            _capi.call("amc3d_fused_sa_backward_assemble", C, O, ptr(G1), ptr(mom), ptr(red), ptr(wp), ptr(QV), ptr(c1wx),
+                       ptr(sxx), ptr(wc), ptr(dWp), st)
+        dWp.addmm_(c1wx, sxx, alpha=-1.0)                    # - diag(c1) W' S_xx  (the c0 column meets a zero row)
+        dfT = X @ wc                                         # A W_f - (cnt f) Q_ff - dpsum Q_fd^T - cnt v_f     (B*N, C)
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
-    dW = torch.cat([dWp[:, C:], dWp[:, :C]], 1).reshape(wshape)
+    dW = torch.cat([dWp[:, C:Kq], dWp[:, :C]], 1).reshape(wshape)
     df = torch.empty((B, C, N), dtype=torch.float32, device=dev)
     with _capi.guard(fT):
         _capi.call("amc3d_transpose_batched", B, N, C, ptr(dfT), ptr(df), stream(fT))
-    return (df, dW, dgamma.float(), dbeta.float(), None, None, None, None, None, None, None)
+    return (df, dW, dgamma, dbeta, None, None, None, None, None, None, None)

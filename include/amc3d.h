@@ -205,6 +205,21 @@ int amc3d_fused_sa_moments(int b, int n, int m, int nsample, float radius, int n
                            const float *xyz, const float *new_xyz, const int *idx, float *cnt, int ld_cnt,
                            float *dpsum, int ld_dps, double *mom, void *stream);
 
+/* The small algebra between the two GEMMs of the backward, as two launches instead of ~30 torch ones
+ * (Kq = C + 3, Kp = C + 8, Kc = O + C + 4; w_packed (O, Kp) as in the forward; small matrices padded to Kp with zeros
+ * so that every library GEMM dimension stays a multiple of 8):
+ *  _backward_coefs     c1wx (O, Kp) = [ c1 (.) W' | c0 | 0 ] with ghat = gamma invstd, c1 = ghat invstd dgamma / P,
+ *                      c0 = ghat dbeta / P - c1 mean in FP64 (P = positions = B*M*nsample); dgamma, dbeta (O) f32.
+ *  _backward_assemble  from g1 = f^T X (C, Kc), mom, qv = W'^T c1wx (Kp, Kp) = [Q | v | 0]:  sxx (Kp, Kp) the second
+ *                      moments, wc (Kc, C) = [W_f; -Q_ff^T; -Q_fd^T; -v_f^T]  (df = X wc),
+ *                      dwp (O, Kp) = [A^T f | wdp | 0] - c0 (x) S_x. */
+int amc3d_fused_sa_backward_coefs(int c, int o, double positions, const float *gamma, const float *invstd,
+                                  const float *mean, const double *dbeta_dgamma_wdp, const float *w_packed,
+                                  float *c1wx, float *dgamma, float *dbeta, void *stream);
+int amc3d_fused_sa_backward_assemble(int c, int o, const float *g1, const double *mom,
+                                     const double *dbeta_dgamma_wdp, const float *w_packed, const float *qv,
+                                     const float *c1wx, float *sxx, float *wc, float *dwp, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * Input side: voxel hash and crop distances of the dataset code
  * ------------------------------------------------------------------------------------- */
