@@ -592,23 +592,31 @@ fused_sa_fwd_kernel(const FusedFwdArgs a) {
     }
 }
 
-// BatchNorm statistics from the sums: mean, biased variance, 1/sqrt(var + eps)
-__global__ void fused_sa_stats_kernel(int O, double count, float eps, const double *__restrict__ gsum,
-                                      const double *__restrict__ gsumsq, float *__restrict__ mean,
-                                      float *__restrict__ var, float *__restrict__ invstd) {
-    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+// BatchNorm statistics from the sums: mean, biased variance, 1/sqrt(var + eps); one warp per channel over the replicas
+__global__ void __launch_bounds__(128)
+fused_sa_stats_kernel(int O, double count, float eps, const double *__restrict__ gsum,
+                      const double *__restrict__ gsumsq, float *__restrict__ mean,
+                      float *__restrict__ var, float *__restrict__ invstd) {
+    const int o = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (o >= O) return;
     double s1 = 0.0, s2 = 0.0;
-    for (int r = 0; r < FS_REPL; ++r) {
+    for (int r = lane; r < FS_REPL; r += 32) {
         s1 += gsum[(long long)r * 2 * O + o];
         s2 += gsumsq[(long long)r * 2 * O + o];
     }
-    const double m = s1 / count;
-    double v = s2 / count - m * m;
-    if (v < 0.0) v = 0.0;
-    mean[o] = (float)m;
-    var[o] = (float)v;
-    invstd[o] = (float)(1.0 / sqrt(v + (double)eps));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+    }
+    if (lane == 0) {
+        const double m = s1 / count;
+        double v = s2 / count - m * m;
+        if (v < 0.0) v = 0.0;
+        mean[o] = (float)m;
+        var[o] = (float)v;
+        invstd[o] = (float)(1.0 / sqrt(v + (double)eps));
+    }
 }
 
 // out[b, o, m] = relu((ysel[b*M + m, o] - mean[o]) * invstd[o] * gamma[o] + beta[o]); 32 x 32 transposing tiles
@@ -718,7 +726,7 @@ extern "C" int amc3d_fused_sa_forward(int b, int n, int m, int c, int o, int nsa
         return rc;
     }
     const double count = (double)b * m * nsample;
-    fused_sa_stats_kernel<<<div_up(o, 128), 128, 0, st>>>(o, count, eps, sums, sums + o, mean, var, invstd);
+    fused_sa_stats_kernel<<<div_up(o, 4), 128, 0, st>>>(o, count, eps, sums, sums + o, mean, var, invstd);
     dim3 fgrid(div_up(m, 32), div_up(o, 32), b);
     fused_sa_finalize_kernel<<<fgrid, 256, 0, st>>>(b, m, o, ysel, mean, invstd, gamma, beta, out);
     return check_launch("fused_sa_forward");
