@@ -5,16 +5,16 @@
 // written and re-read per step at BASELINE config 2 — is never materialised.
 //
 //   forward    y[o, p] = sum_k W'[o, k] x[p, k]        x[p] = [ f[b, idx[p], 0..C) | (xyz[idx[p]] - q) / r | 0 ]
-//              as tcgen05 MMAs (kind::tf32, FP32 accumulators in TMEM):  M = 128 output channels, N = 128 grouped
-//              positions (= 128 / ns queries), K = C + 8 in 128-byte chunks.  The B operand (positions x K) is
-//              GATHERED: 8 lanes fetch one neighbour's 128 contiguous bytes of the channel-contiguous (B, N, C)
-//              feature copy and store them into the 128B-swizzled K-major tile the MMA reads; the A operand (W')
-//              is staged the same way.  The epilogue thread that owns TMEM lane o holds the ns conv outputs of a
-//              query in registers, so max / arg-max over the neighbourhood and the BatchNorm sums are
-//              thread-local.  BatchNorm + ReLU are monotone in y (increasing for gamma >= 0, decreasing
-//              otherwise), hence  max_s relu(bn(y_s)) = relu(bn(max_s y_s))  (min for gamma < 0): ONE pass over
-//              the gathered rows gives the pre-normalisation extreme per (query, channel) and the statistics;
-//              a small second kernel normalises.
+//              as tcgen05 MMAs (kind::tf32, FP32 accumulators in TMEM):  M = 128 output channels, N = 256 grouped
+//              positions (= 256 / ns queries; 128 in the 3xTF32 mode), K = C + 8 in 128-byte chunks.  The B operand
+//              (positions x K) is GATHERED: 8 lanes fetch one neighbour's 128 contiguous bytes of the
+//              channel-contiguous (B, N, C) feature copy with cp.async straight into the 128B-swizzled K-major tile
+//              the MMA reads; the A operand (W') arrives as ready-made tiles by bulk copy.  The epilogue thread that
+//              owns TMEM lane o holds the ns conv outputs of a query in registers, so max / arg-max over the
+//              neighbourhood and the BatchNorm sums are thread-local.  BatchNorm + ReLU are monotone in y
+//              (increasing for gamma >= 0, decreasing otherwise), hence  max_s relu(bn(y_s)) = relu(bn(max_s y_s))
+//              (min for gamma < 0): ONE pass over the gathered rows gives the pre-normalisation extreme per
+//              (query, channel) and the statistics; a small second kernel normalises.
 //   precision  X3 = false: operands are read as TF32 by the tensor core (what the reference's cuDNN convolution
 //              does on Ampere and later: torch.backends.cudnn.allow_tf32 defaults to True);
 //              X3 = true: error-compensated 3 x TF32 (hi*hi + lo*hi + hi*lo, hi = rna(x), lo = x - hi), FP32-faithful

@@ -337,6 +337,32 @@ def measure_fp32_tflops(dev):
     return best
 
 
+def measure_hbm_directional(dev, gib=1.0):
+    """Write-only, read-only and copy bandwidth of this GPU, live (torch fill / sum / copy_ over `gib` GiB, best of 5,
+    CUDA events): context for the grouping pair, whose forward is ~97 % writes and whose backward is ~97 % reads of
+    HBM — the contract's roofline denominator stays the copy figure of MEASURED_PEAKS.json."""
+    n = int(gib * (1 << 30) / 4)
+    a = torch.empty(n, dtype=torch.float32, device=dev)
+    b = torch.empty(n, dtype=torch.float32, device=dev)
+    res = {}
+    for name, fn, nbytes in (("write_only", lambda: a.fill_(1.0), 4 * n), ("read_only", lambda: a.sum(), 4 * n),
+                             ("copy", lambda: b.copy_(a), 8 * n)):
+        best = 0.0
+        for i in range(7):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                best = max(best, nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+        res[name + "_gbs"] = round(best, 1)
+    del a, b
+    torch.cuda.empty_cache()
+    res["how"] = f"torch fill_ / sum / copy_ over {gib} GiB fp32, best of 5, CUDA events (library kernels, context only)"
+    return res
+
+
 def count_evaluated_pairs(replay):
     """One extra, untimed step with the counting instantiations of the culled search kernels
     (amc3d_search_stats): distance evaluations actually issued, per entry point."""
@@ -725,6 +751,7 @@ def run_ours(args):
     hbm_peak, peak_src = measured_peaks()
     fp32_nominal = fp32_peak_tflops()
     fp32_measured = measure_fp32_tflops(dev)
+    hbm_dir = measure_hbm_directional(dev) if world == 1 else None
     kernels = []
     for name, d in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
         row = {"entry": name, "calls": d["calls"], "ms": round(d["ms"], 4), "share": round(d["ms"] / total_ms, 4)}
@@ -817,6 +844,7 @@ def run_ours(args):
                             "events; search rows report distance evaluations counted inside the kernels (8 FLOP each) "
                             "against it — the rest of their issue slots is box tests and top-k maintenance, see "
                             "profiles/r02_search_ncu.md for issue-slot utilisation"},
+            "hbm_directional": hbm_dir,
             "kernels": kernels, "kernel_ms_per_step": round(total_ms, 3), "cpu_baseline": cpu_baseline,
             "ref_gpu": ref_gpu, "fused_operator": fused, "fused_step": fused_step}
     print(json.dumps(line), flush=True)
