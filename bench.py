@@ -652,7 +652,7 @@ def run_ours(args):
 
     # eager arm (every operator call issued from Python each step) — reported beside the graph arm
     e2e_steps = max(1, min(args.steps, 10))
-    eager_ms, _ = timed(e2e_steps, False, False)
+    eager_ms = min(timed(e2e_steps, False, False)[0] for _ in range(2))     # best of two passes (allocator warm-up)
     one_step(True, False)
     eager_e2e_ms, last_loss = timed(e2e_steps, True, False)
     eager = {"ms_per_step": eager_ms / e2e_steps, "e2e_ms_per_step": eager_e2e_ms / e2e_steps, "steps": e2e_steps}
