@@ -62,8 +62,11 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Bounded: a protocol error must surface as a failed launch (cudaErrorLaunchFailure through amc3d's error path), never
+// as a kernel that spins for ever.  try_wait suspends the thread for a hardware time slice per attempt, so 2^24 failed
+// attempts are many seconds — four orders of magnitude beyond the longest legitimate wait in this kernel.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok = 0;
+    uint32_t ok = 0, tries = 0;
     while (!ok) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -72,6 +75,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "=r"(ok)
             : "r"(bar), "r"(parity)
             : "memory");
+        if (!ok && ++tries > (1u << 24)) __trap();
     }
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
