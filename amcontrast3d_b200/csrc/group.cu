@@ -398,18 +398,41 @@ interp_fwd_tma_kernel(int C, int M, int N, const float *__restrict__ srcT, const
     const float *src = srcT + (long long)b * M * C + cc;
     const int wpos = min(32, npos - warp * 32);
     float *trow = tile + lane * FWD_LD + warp * 32;
-    for (int o = 0; o * 4 < wpos; ++o) {
-        float v[4];
+    if (wpos == 32) {
+        // full warp tile: four batches of 8 positions, the 24 gathers of a batch in flight together
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int p = warp * 32 + o * 4 + u;
-            const int i0 = s_idx[3 * p], i1 = s_idx[3 * p + 1], i2 = s_idx[3 * p + 2];
-            const float w0 = s_w[3 * p], w1 = s_w[3 * p + 1], w2 = s_w[3 * p + 2];
-            const float f0 = __ldg(src + (long long)i0 * C), f1 = __ldg(src + (long long)i1 * C),
-                        f2 = __ldg(src + (long long)i2 * C);
-            v[u] = __fmaf_rn(w2, f2, __fmaf_rn(w0, f0, __fmul_rn(w1, f1)));   // interpolate_gpu.cu:103 as nvcc contracts it
+        for (int h = 0; h < 4; ++h) {
+            float f[8][3];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int p = warp * 32 + h * 8 + u;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) f[u][k] = __ldg(src + (long long)s_idx[3 * p + k] * C);
+            }
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int p = warp * 32 + h * 8 + u;
+                // interpolate_gpu.cu:103 as nvcc contracts it
+                v[u] = __fmaf_rn(s_w[3 * p + 2], f[u][2], __fmaf_rn(s_w[3 * p], f[u][0], __fmul_rn(s_w[3 * p + 1], f[u][1])));
+            }
+            *reinterpret_cast<float4 *>(trow + h * 8) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4 *>(trow + h * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
         }
-        *reinterpret_cast<float4 *>(trow + o * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+        for (int o = 0; o * 4 < wpos; ++o) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int p = warp * 32 + o * 4 + u;
+                const int i0 = s_idx[3 * p], i1 = s_idx[3 * p + 1], i2 = s_idx[3 * p + 2];
+                const float w0 = s_w[3 * p], w1 = s_w[3 * p + 1], w2 = s_w[3 * p + 2];
+                const float f0 = __ldg(src + (long long)i0 * C), f1 = __ldg(src + (long long)i1 * C),
+                            f2 = __ldg(src + (long long)i2 * C);
+                v[u] = __fmaf_rn(w2, f2, __fmaf_rn(w0, f0, __fmul_rn(w1, f1)));   // interpolate_gpu.cu:103 as nvcc contracts it
+            }
+            *reinterpret_cast<float4 *>(trow + o * 4) = make_float4(v[0], v[1], v[2], v[3]);
+        }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
