@@ -125,6 +125,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool v
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16u : 0u) : "memory");
 }
 
+
 template <bool X3>
 __device__ __forceinline__ void fs_store(unsigned char *hi, unsigned char *lo, uint32_t off, float4 v) {
     if (X3) {
@@ -173,16 +174,22 @@ __device__ __forceinline__ void tmem_ld_query<16>(uint32_t taddr, float (&v)[16]
 
 // W' (O, Kp) -> operand tiles: block (slice j, chunk kc) holds rows j*128 .. j*128+127, columns kc*32 .. kc*32+31 with the
 // 16-byte slot c of row r at r*128 + ((c ^ (r & 7)) << 4), zeros outside the matrix; X3 adds the lo = x - rna(x) tile.
+// Rows with gamma < 0 are NEGATED (exact): the accumulators then hold t = sign(gamma) y, whose maximum over the
+// neighbourhood is what the pooled output needs for either sign, and the epilogue has no per-element sign to apply.
 template <bool X3>
 __global__ void __launch_bounds__(256)
-fused_sa_wprep_kernel(int O, int Kp, int nchunks, const float *__restrict__ Wp, float *__restrict__ Wsw) {
+fused_sa_wprep_kernel(int O, int Kp, int nchunks, const float *__restrict__ Wp, const float *__restrict__ gamma,
+                      float *__restrict__ Wsw) {
     const int blk = blockIdx.x, j = blk / nchunks, kc = blk % nchunks;
     unsigned char *dst = reinterpret_cast<unsigned char *>(Wsw) + (size_t)blk * (X3 ? 2 : 1) * FS_MT * FS_ROWB;
     for (int e = threadIdx.x; e < FS_MT * 8; e += 256) {
         const int r = e >> 3, c = e & 7;
         const int o = j * 128 + r, k0 = kc * 32 + c * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (o < O && k0 < Kp) v = __ldg(reinterpret_cast<const float4 *>(Wp + (long long)o * Kp + k0));
+        if (o < O && k0 < Kp) {
+            v = __ldg(reinterpret_cast<const float4 *>(Wp + (long long)o * Kp + k0));
+            if (__ldg(gamma + o) < 0.f) v = make_float4(-v.x, -v.y, -v.z, -v.w);
+        }
         fs_store<X3>(dst, dst + FS_MT * FS_ROWB, sw128_off(r, c), v);
     }
 }
@@ -337,6 +344,17 @@ fused_sa_fwd_kernel(const FusedFwdArgs a) {
                 if (X3) rowv[i] = row;
                 livemask |= (live ? 1u : 0u) << i;
             }
+            // TF32 path: global address of this thread's 16 bytes of the NEXT chunk in each of its rows (advanced by 128
+            // bytes per chunk) and the copy size that makes a dead row a zero-fill: the chunk loop is copy + add
+            unsigned long long gsrc[X3 ? 1 : NPASS];
+            uint32_t gsz[X3 ? 1 : NPASS];
+            if (!X3) {
+#pragma unroll
+                for (int i = 0; i < NPASS; ++i) {
+                    gsrc[X3 ? 0 : i] = reinterpret_cast<unsigned long long>(a.fT + xoff[i]);
+                    gsz[X3 ? 0 : i] = ((livemask >> i) & 1u) ? 16u : 0u;
+                }
+            }
             if (item + (int)gridDim.x < nitems) load_idx(item + (int)gridDim.x, nxt);   // in flight during this item's chunks
             if (a.dbg) t_set += clock64() - ts0;
             for (int kc = 0; kc < nchunks; ++kc) {
@@ -357,12 +375,17 @@ fused_sa_fwd_kernel(const FusedFwdArgs a) {
                         for (int i = 0; i < NPASS; ++i)
                             *reinterpret_cast<float4 *>(xt + soff0 + (uint32_t)i * (FS_RPP * FS_ROWB)) = dp_stage[sb * NT + i * FS_RPP + rsub];
                         mbar_arrive(fs_smem(&dp_free[sb]));
-                    } else {
+                    } else if (featk) {
 #pragma unroll
                         for (int i = 0; i < NPASS; ++i) {
-                            const bool ok = featk && ((livemask >> i) & 1u);
-                            cp_async16(xs + soff0 + (uint32_t)i * (FS_RPP * FS_ROWB), a.fT + xoff[i] + kc * 32, ok);
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(xs + soff0 + (uint32_t)i * (FS_RPP * FS_ROWB)),
+                                         "l"(gsrc[X3 ? 0 : i]), "r"(gsz[X3 ? 0 : i])
+                                         : "memory");
+                            gsrc[X3 ? 0 : i] += FS_ROWB;
                         }
+                    } else {                                       // past the features: zeros (the source is not read)
+#pragma unroll
+                        for (int i = 0; i < NPASS; ++i) cp_async16(xs + soff0 + (uint32_t)i * (FS_RPP * FS_ROWB), a.fT, false);
                     }
                 } else {
                     // 3xTF32: through registers (split into hi = rna(x) and lo = x - hi), relative coordinates inline
@@ -541,7 +564,7 @@ fused_sa_fwd_kernel(const FusedFwdArgs a) {
             const int o = (item - (int)tile * nsl) * FS_MT + lane_o;
             if (o != co) { flush(); co = o; }
             const bool live = o < a.O;
-            // gamma < 0: BatchNorm + ReLU decrease in y, the pooled maximum sits at the MINIMUM of y: track max of -y
+            // gamma < 0: BatchNorm + ReLU decrease in y, the pooled maximum sits at the MINIMUM of y = the maximum of -y
             const float sgn = (live && __ldg(a.gamma + o) < 0.f) ? -1.f : 1.f;
             const long long te0 = a.dbg ? clock64() : 0;
             mbar_wait(fs_smem(&acc_full[buf]), (uint32_t)((it >> 1) & 1));
@@ -551,8 +574,9 @@ fused_sa_fwd_kernel(const FusedFwdArgs a) {
             for (int qi = half; qi < QPT; qi += 2) {
                 float v[NS];
                 tmem_ld_query<NS>(lane_addr + (uint32_t)(buf * NT + qi * NS), v);   // warp-uniform control flow up to here
-                // two independent (max, arg-max) chains over the halves, four partial sums: no branches, short chains
-                float m0 = v[0] * sgn, m1 = v[NS / 2] * sgn;
+                // v = sign(gamma) y (the weight rows carry the sign).  Two independent (max, arg-max) chains over the
+                // halves, four partial sums: no branches, short chains
+                float m0 = v[0], m1 = v[NS / 2];
                 int i0 = 0, i1 = NS / 2;
                 float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
 #pragma unroll
@@ -562,11 +586,10 @@ fused_sa_fwd_kernel(const FusedFwdArgs a) {
                     s1b += y;
                     s2a = fmaf(x, x, s2a);
                     s2b = fmaf(y, y, s2b);
-                    const float tx = x * sgn, ty = y * sgn;
-                    const bool gx = tx > m0, gy = ty > m1;
-                    m0 = gx ? tx : m0;
+                    const bool gx = x > m0, gy = y > m1;
+                    m0 = gx ? x : m0;
                     i0 = gx ? s : i0;
-                    m1 = gy ? ty : m1;
+                    m1 = gy ? y : m1;
                     i1 = gy ? s + NS / 2 : i1;
                 }
                 const bool g2 = m1 > m0;                           // ties keep the lower sample index
@@ -574,7 +597,7 @@ fused_sa_fwd_kernel(const FusedFwdArgs a) {
                 const int bi = g2 ? i1 : i0;
                 const long long qg = q0 + qi;
                 if (live && qg < (long long)Q) {
-                    csum += s1a + s1b;
+                    csum += (s1a + s1b) * sgn;
                     csq += s2a + s2b;
                     a.ysel[qg * a.O + o] = best;
                     a.arg[qg * a.O + o] = (unsigned char)bi;
@@ -673,7 +696,7 @@ static int launch_fused_fwd(FusedFwdArgs &a, cudaStream_t st) {
     const size_t smem = fixed + a.stages * slot + 1024 + (X3 ? 0 : 2 * NT * sizeof(float4));   // + alignment slack + dp staging
     cudaError_t e = cudaFuncSetAttribute(fused_sa_fwd_kernel<NS, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    fused_sa_wprep_kernel<X3><<<a.nslices * nchunks, 256, 0, st>>>(a.O, a.Kp, nchunks, a.Wp, const_cast<float *>(a.Wsw));
+    fused_sa_wprep_kernel<X3><<<a.nslices * nchunks, 256, 0, st>>>(a.O, a.Kp, nchunks, a.Wp, a.gamma, const_cast<float *>(a.Wsw));
     static long long *dbg_dev = nullptr;
     a.dbg = nullptr;
     if (env_dbg) {

@@ -652,10 +652,23 @@ def run_ours(args):
 
     # eager arm (every operator call issued from Python each step) — reported beside the graph arm
     e2e_steps = max(1, min(args.steps, 10))
-    eager_ms = min(timed(e2e_steps, False, False)[0] for _ in range(2))     # best of two passes (allocator warm-up)
-    one_step(True, False)
-    eager_e2e_ms, last_loss = timed(e2e_steps, True, False)
-    eager = {"ms_per_step": eager_ms / e2e_steps, "e2e_ms_per_step": eager_e2e_ms / e2e_steps, "steps": e2e_steps}
+    # (Python's cyclic collector is paused for these loops, as timeit does: an eager step creates a few hundred
+    # tensors and autograd nodes, and a generation-2 collection in the middle of ten steps is milliseconds)
+    import gc
+    gc.collect()
+    gc.disable()
+    try:
+        eager_passes = [timed(e2e_steps, False, False)[0] / e2e_steps for _ in range(3)]
+        one_step(True, False)
+        e2e_passes = [timed(e2e_steps, True, False) for _ in range(2)]
+    finally:
+        gc.enable()
+    eager_ms = min(eager_passes) * e2e_steps
+    eager_e2e_ms, last_loss = min(e2e_passes, key=lambda t: t[0])
+    eager = {"ms_per_step": eager_ms / e2e_steps, "e2e_ms_per_step": eager_e2e_ms / e2e_steps, "steps": e2e_steps,
+             "passes_ms_per_step": [round(x, 3) for x in eager_passes],
+             "e2e_passes_ms_per_step": [round(t[0] / e2e_steps, 3) for t in e2e_passes],
+             "note": "best of the passes shown; Python's cyclic GC paused during the loops"}
 
     l0 = _capi.LAUNCHES
     one_step(False, False)
