@@ -596,7 +596,8 @@ int fps_launch(int b, int n, int m, int log2bs, const float *xyz, float *temp, i
     // of sending warps — so more warps only when the points no longer fit 4 warps' registers)
     int cs = n > 1536 ? 16 : (n > 768 ? 8 : (n > 192 ? 4 : 1));
     int nw = 4;
-    if (div_up(n, cs * nw * 32) > 32) {
+    if (div_up(n, cs * nw * 32) > 28) {            // measured crossover (tools/diag/fps_nw.py): 40 000 pts 0.29 vs 0.35 us/pick,
+                                                   // 64 000 pts 0.40 vs 0.38 us/pick for 4 vs 8 warps
         nw = 8;
         if (div_up(n, cs * nw * 32) > 24) nw = 16;
     }
