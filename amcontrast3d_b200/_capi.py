@@ -61,6 +61,7 @@ SIGNATURES = {
     "amc3d_fused_sa_backward_scatter": [_I, _I, _I, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P],
     "amc3d_fused_sa_backward_coefs": [_I, _I, ctypes.c_double, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "amc3d_fused_sa_backward_assemble": [_I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "amc3d_debug_fastdiv": [ctypes.c_uint, ctypes.c_uint],
     "amc3d_fused_sa_moments": [_I, _I, _I, _I, _F, _I, _P, _P, _P, _P, _I, _P, _I, _P, _P],
     "amc3d_voxel_keys": [_LL, ctypes.c_double, _P, _P, _P, _P],
     "amc3d_crop_dist2": [_LL, _P, _LL, _P, _P],
@@ -96,7 +97,7 @@ SIGNATURES = {
     "amc3d_refine_forward": [_I, _I, _I, _P, _P, _P, _F, _F, _F, _P, _P, _P],
     "amc3d_refine_backward": [_I, _I, _I, _P, _P, _P, _F, _F, _F, _P, _P],
 }
-_RESTYPES = {"amc3d_arch": c_char_p, "amc3d_last_error": c_char_p}
+_RESTYPES = {"amc3d_arch": c_char_p, "amc3d_last_error": c_char_p, "amc3d_debug_fastdiv": ctypes.c_uint}
 
 
 class Amc3dError(RuntimeError):

@@ -1038,3 +1038,11 @@ extern "C" int amc3d_fused_sa_backward_assemble(int c, int o, const float *g1, c
         o, c, g1, mom, dbeta_dgamma_wdp + 2 * (size_t)o, w_packed, qv, c1wx, sxx, wc, dwp);
     return check_launch("fused_sa_backward_assemble");
 }
+
+// Host-side check of the division-free index arithmetic the fused forward uses on the device (FastDiv): returns
+// n / d computed the way the kernel does (multiply-high by the precomputed magic, shift).  Valid for n < 2^31, d >= 1.
+extern "C" unsigned int amc3d_debug_fastdiv(unsigned int n, unsigned int d) {
+    const FastDiv f = make_fastdiv(d);
+    if (f.one) return n;
+    return (unsigned int)(((unsigned long long)n * f.m) >> 32) >> f.s;
+}

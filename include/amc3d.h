@@ -220,6 +220,10 @@ int amc3d_fused_sa_backward_assemble(int c, int o, const float *g1, const double
                                      const double *dbeta_dgamma_wdp, const float *w_packed, const float *qv,
                                      const float *c1wx, float *sxx, float *wc, float *dwp, void *stream);
 
+/* Test hook (host code only, no launch): n / d evaluated with the multiply-high constants the fused forward uses for
+ * its per-item index arithmetic; n < 2^31, d >= 1. */
+unsigned int amc3d_debug_fastdiv(unsigned int n, unsigned int d);
+
 /* ---------------------------------------------------------------------------------------
  * Input side: voxel hash and crop distances of the dataset code
  * ------------------------------------------------------------------------------------- */

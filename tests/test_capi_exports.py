@@ -88,3 +88,21 @@ def test_reference_facing_names_exist():
     # loss / ambiguity heads must stay parameter- and buffer-free (checkpoint compatibility)
     assert len(ContrastHead().state_dict()) == 0 and len(AmbiguityHead().state_dict()) == 0
     assert ContrastHead().stages == [('up', 0), ('up', 1), ('up', 2), ('up', 3)]
+
+
+def test_division_free_index_arithmetic_of_the_fused_forward():
+    """FastDiv (csrc/fused_sa.cu): multiply-high magic for n / d, n < 2^31 — every divisor the kernel can meet
+    (queries per scene, output-channel slices) against integer division, on the host copy of the same code"""
+    import random
+    from amcontrast3d_b200 import _capi
+    f = _capi.load().amc3d_debug_fastdiv
+    rng = random.Random(7)
+    divisors = list(range(1, 1200)) + [2 ** k + d for k in range(1, 25) for d in (-1, 0, 1)] + \
+        [rng.randrange(1, 1 << 25) for _ in range(1500)] + [6000, 24000, 93, 375, 1500, 16000, 64000]
+    for d in divisors:
+        if d < 1:
+            continue
+        for n in (0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, 7 * d + 3, (1 << 31) - 1, (1 << 31) - d, (1 << 25) - 1,
+                  rng.randrange(0, 1 << 31), rng.randrange(0, 1 << 25)):
+            if 0 <= n < (1 << 31):
+                assert f(n, d) == n // d, (n, d)
