@@ -115,6 +115,7 @@ def _torch_composition(q, p, f, idx, w, gamma, beta, radius, arg, eps=1e-5):
     (2, 375, 375, 512, 512, 32, 0.8),       # level 3: four output-channel slices per position tile
     (3, 93, 93, 1024, 1024, 32, 1.6),       # level 4; 3 * 93 queries: a ragged last tile
     (2, 500, 500, 40, 72, 16, 0.3),         # nsample 16, channel counts off the 32 / 128 grids
+    (2, 300, 300, 264, 72, 32, 0.3),        # one output slice whose weights do not stay resident (C > 216)
 ])
 def test_fused_operator_vs_fp64_composition(B, N, M, C, O, ns, radius):
     from amcontrast3d_b200 import scenes

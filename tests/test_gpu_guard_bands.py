@@ -43,7 +43,9 @@ class _GuardedTorch:
 
 
 @pytest.mark.parametrize("B,N,M,C,O,ns,prec", [(3, 333, 333, 40, 72, 16, "tf32x3"), (2, 500, 125, 64, 200, 32, "tf32"),
-                                               (1, 260, 65, 264, 136, 32, "tf32x3"), (2, 129, 129, 8, 8, 16, "tf32")])
+                                               (1, 260, 65, 264, 136, 32, "tf32x3"), (2, 129, 129, 8, 8, 16, "tf32"),
+                                               # one output slice whose weights do NOT stay resident (C > 216), both precisions
+                                               (1, 200, 200, 264, 72, 32, "tf32"), (1, 200, 200, 264, 72, 16, "tf32x3")])
 def test_fused_operator_writes_stay_inside_its_buffers(monkeypatch, B, N, M, C, O, ns, prec):
     from amcontrast3d_b200 import scenes
     from amcontrast3d_b200.layers import ball_query, fused, _fused_backward
