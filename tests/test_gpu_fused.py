@@ -89,7 +89,7 @@ def test_fused_operator_vs_reference_golden(name):
     assert int(bn.num_batches_tracked) == 1
 
 
-def _torch_composition(q, p, f, idx, w, gamma, beta, radius, arg, eps=1e-5):
+def _torch_composition(q, p, f, idx, w, gamma, beta, radius, arg, eps=1e-5, normalize_dp=True):
     """the module composition in FP64 on the GPU (gather + einsum + batch statistics + relu + max).  The max is
     taken at the sample `arg` (B,O,M) the operator chose; the second return value is how far below the true
     maximum that choice is.  Max-pooling over values that carry rounding errors has no unique arg-max: two
@@ -99,7 +99,8 @@ def _torch_composition(q, p, f, idx, w, gamma, beta, radius, arg, eps=1e-5):
     M, ns = idx.shape[1], idx.shape[2]
     flat = idx.reshape(B, 1, -1).long()
     dp = torch.gather(p.transpose(1, 2), 2, flat.expand(-1, 3, -1)).reshape(B, 3, M, ns)
-    dp = ((dp - q.transpose(1, 2).unsqueeze(-1)) * (1.0 / np.float32(radius))).to(f.dtype)     # FP32 values, as the operator forms them
+    scale = (1.0 / np.float32(radius)) if normalize_dp else 1.0
+    dp = ((dp - q.transpose(1, 2).unsqueeze(-1)) * scale).to(f.dtype)     # FP32 values, as the operator forms them
     fj = torch.gather(f, 2, flat.expand(-1, C, -1)).reshape(B, C, M, ns)
     y = torch.einsum("oc,bcps->bops", w, torch.cat([dp, fj], 1))
     mean = y.mean(dim=(0, 2, 3), keepdim=True)
@@ -151,6 +152,37 @@ def test_fused_operator_vs_fp64_composition(B, N, M, C, O, ns, radius):
         gtol = tol if prec == "tf32x3" else 5e-3
         for a, b, what in zip(mine, ref_leaves, ("df", "dW", "dgamma", "dbeta")):
             assert rel_err(a.grad.cpu().numpy(), b.grad.cpu().numpy()) < gtol, (prec, what)
+
+
+def test_fused_operator_without_normalised_relative_coordinates_and_single_query():
+    """normalize_dp = False (QueryAndGroup's other setting) and the smallest launch there is: one query"""
+    from amcontrast3d_b200 import scenes
+    from amcontrast3d_b200.layers import ball_query
+    from amcontrast3d_b200.layers.fused import FusedGroupConvBNReLUMax
+    for B, N, M, C, O, ns, radius in ((2, 400, 400, 32, 48, 32, 0.3), (1, 64, 1, 16, 8, 16, 0.5)):
+        xyz, _ = scenes.batch_of_scenes(B, N, "surface", first_scene=11)
+        p = torch.from_numpy(xyz).cuda()
+        q = p[:, :M].contiguous()
+        g = torch.Generator(device="cuda").manual_seed(23)
+        f = torch.randn(B, C, N, device="cuda", generator=g)
+        w = torch.randn(O, C + 3, device="cuda", generator=g) / (C + 3) ** 0.5
+        gamma = 1 + 0.1 * torch.randn(O, device="cuda", generator=g)
+        gamma[::3] *= -1
+        beta = 0.1 * torch.randn(O, device="cuda", generator=g)
+        go = torch.randn(B, O, M, device="cuda", generator=g)
+        idx = ball_query(radius, ns, p, q)
+        mine = [t.clone().requires_grad_(True) for t in (f, w, gamma, beta)]
+        out, mean, var = FusedGroupConvBNReLUMax.apply(*mine, q, p, idx, radius, False, 1e-5, "tf32x3")
+        arg = out.grad_fn.saved_tensors[7].view(B, M, O).transpose(1, 2).clone()
+        out.backward(go)
+        ref_leaves = [t.double().requires_grad_(True) for t in (f, w, gamma, beta)]
+        ref_out, below = _torch_composition(q.double(), p.double(), ref_leaves[0], idx, *ref_leaves[1:], radius, arg,
+                                            normalize_dp=False)
+        ref_out.backward(go.double())
+        assert float(below) <= 2e-5
+        assert rel_err(out.detach().cpu().numpy(), ref_out.detach().cpu().numpy()) < TOL
+        for a, b, what in zip(mine, ref_leaves, ("df", "dW", "dgamma", "dbeta")):
+            assert rel_err(a.grad.cpu().numpy(), b.grad.cpu().numpy()) < TOL, what
 
 
 def test_unsupported_configurations_use_the_module_composition():
