@@ -848,7 +848,7 @@ fused_sa_bwd_scatter_kernel(int B, int N, int M, int O, int NS, float inv_radius
 __global__ void __launch_bounds__(256)
 fused_sa_moments_kernel(int B, int N, int M, int NS, float inv_radius, const float *__restrict__ xyz,
                         const float *__restrict__ qxyz, const int *__restrict__ idx, float *__restrict__ cnt, int ldc,
-                        float *__restrict__ dpsum, int ldd, double *__restrict__ mom) {
+                        float *__restrict__ dpsum, int ldd, double *__restrict__ mom, int packed) {
     const long long P = (long long)B * M * NS;
     const long long p = (long long)blockIdx.x * 256 + threadIdx.x;
     float d[3] = {0.f, 0.f, 0.f};
@@ -858,9 +858,15 @@ fused_sa_moments_kernel(int B, int N, int M, int NS, float inv_radius, const flo
         const long long row = b * N + __ldg(idx + p);
 #pragma unroll
         for (int j = 0; j < 3; ++j) d[j] = (__ldg(xyz + row * 3 + j) - __ldg(qxyz + q * 3 + j)) * inv_radius;
-        atomicAdd(cnt + row * ldc, 1.f);
+        if (packed) {                                  // [dpsum | cnt] are four consecutive, 16-byte aligned floats: one reduction
+            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dpsum + row * ldd), "f"(d[0]), "f"(d[1]), "f"(d[2]),
+                         "f"(1.f)
+                         : "memory");
+        } else {
+            atomicAdd(cnt + row * ldc, 1.f);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) atomicAdd(dpsum + row * ldd + j, d[j]);
+            for (int j = 0; j < 3; ++j) atomicAdd(dpsum + row * ldd + j, d[j]);
+        }
     }
     float v[12] = {d[0], d[1], d[2], d[0] * d[0], d[0] * d[1], d[0] * d[2], d[1] * d[0], d[1] * d[1], d[1] * d[2],
                    d[2] * d[0], d[2] * d[1], d[2] * d[2]};
@@ -1006,7 +1012,9 @@ extern "C" int amc3d_fused_sa_moments(int b, int n, int m, int nsample, float ra
     AMC3D_REQUIRE(b >= 0 && n >= 1 && m >= 0 && nsample >= 1, AMC3D_EINVAL, "fused_sa_moments: bad sizes");
     AMC3D_REQUIRE(ld_cnt >= 1 && ld_dps >= 3, AMC3D_EINVAL, "fused_sa_moments: row strides %d, %d", ld_cnt, ld_dps);
     cudaStream_t st = as_stream(stream);
-    if (dpsum + 3 == cnt && ld_cnt == ld_dps) {                     // [dpsum | cnt] side by side: one pass
+    const bool side_by_side = dpsum + 3 == cnt && ld_cnt == ld_dps;
+    const int packed = side_by_side && ld_dps % 4 == 0 && (reinterpret_cast<uintptr_t>(dpsum) & 15) == 0;
+    if (side_by_side) {                                             // [dpsum | cnt] side by side: one pass
         zero_cols(dpsum, (long long)b * n, ld_dps, 4, st);
     } else {
         zero_cols(cnt, (long long)b * n, ld_cnt, 1, st);
@@ -1016,7 +1024,7 @@ extern "C" int amc3d_fused_sa_moments(int b, int n, int m, int nsample, float ra
     const long long P = (long long)b * m * nsample;
     if (P > 0)
         fused_sa_moments_kernel<<<(unsigned)div_up_ll(P, 256), 256, 0, st>>>(b, n, m, nsample, normalize_dp ? 1.0f / radius : 1.0f,
-                                                                              xyz, new_xyz, idx, cnt, ld_cnt, dpsum, ld_dps, mom);
+                                                                              xyz, new_xyz, idx, cnt, ld_cnt, dpsum, ld_dps, mom, packed);
     return check_launch("fused_sa_moments");
 }
 
